@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- smoothed time-steps / second of one sqrt parallel filter + RTS smoother pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl psqrt|reference]
+
+Workload (BASELINE.json metric, SURVEY.md section 8d recipe C1 at the metric's length): random stable
+LGSSM, nx = 4, ny = 2, T = 1e6 per GPU, fp64, one `filter_smoother` pass = one step.  With N > 1
+(torchrun) the sequence is N x 1e6 steps long and time-sharded: local scans, two NCCL all-gathers of
+the shard totals, carry application (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM,
+`e2e` = the same pass through the public API with pinned HOST buffers (H2D of the observations and
+D2H of the smoothed trajectory inside the timed region), `roofline` = the dominant kernel against
+the measured HBM peak, `cpu_baseline` = the NumPy restatement of the reference timed on this
+box's cores.  `--impl reference` times that CPU restatement alone (JAX is not installable here:
+no wheel in /opt/wheelhouse, no network), on the same workload definition.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "sqrt-parallel-smoothers_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+NX, NY = 4, 2
+T_PER_GPU = 1_000_000
+METRIC = "smoothed time-steps/sec, one sqrt parallel filter+RTS smoother pass, T=1e6 per GPU, nx=4, fp64"
+
+
+def algorithmic_bytes_per_step(n):
+    """read one filtering element + write filtered (m, L) + read one smoothing
+    element + write smoothed (m, L) = 8 (7 n^2 + 5 n)."""
+    return 8 * (7 * n * n + 5 * n)
+
+
+def make_lgssm(n, ny, seed=0):
+    rng = np.random.RandomState(seed)
+    Qr, _ = np.linalg.qr(rng.randn(n, n))
+    F = 0.99 * Qr
+    cholQ = 0.1 * (np.tril(rng.rand(n, n)) + np.eye(n))
+    H = rng.randn(ny, n)
+    cholR = 0.5 * (np.tril(rng.rand(ny, ny)) + np.eye(ny))
+    b = 0.1 * rng.randn(n)
+    c = 0.1 * rng.randn(ny)
+    m0 = rng.randn(n)
+    return dict(F=F, cholQ=cholQ, b=b, H=H, cholR=cholR, c=c, m0=m0, L0=np.eye(n))
+
+
+def simulate(model, T, seed):
+    """fp64 simulation of the LGSSM (procedure of the reference's tests/_lgssm.py:89-93)."""
+    rng = np.random.RandomState(seed)
+    n, ny = model["F"].shape[0], model["H"].shape[0]
+    wq = rng.randn(T, n) @ model["cholQ"].T + model["b"]
+    wr = rng.randn(T, ny) @ model["cholR"].T + model["c"]
+    F, H = model["F"], model["H"]
+    x = model["m0"].copy()
+    ys = np.empty((T, ny))
+    Ft = np.ascontiguousarray(F.T)
+    Ht = np.ascontiguousarray(H.T)
+    for k in range(T):
+        x = x @ Ft + wq[k]
+        ys[k] = x @ Ht + wr[k]
+    return ys
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU restatement arm (reference / cpu_baseline)
+# --------------------------------------------------------------------------------------------------
+def _threaded_tria(n_threads):
+    """The oracle's tria with the batch split over host threads (LAPACK releases the GIL)."""
+    import parsmooth_np as O
+    from concurrent.futures import ThreadPoolExecutor
+    base = O.tria
+    pool = ThreadPoolExecutor(n_threads)
+
+    def tria(A):
+        A = np.asarray(A)
+        if A.ndim < 3 or A.shape[0] < 4 * n_threads:
+            return base(A)
+        parts = np.array_split(np.arange(A.shape[0]), n_threads)
+        outs = list(pool.map(lambda idx: base(A[idx[0]:idx[-1] + 1]), [p for p in parts if len(p)]))
+        return np.concatenate(outs, 0)
+
+    return base, tria
+
+
+def cpu_pass_rate(model, T_sample, threads, seed=123):
+    """steps/s of the NumPy restatement of the reference's PARALLEL sqrt filter + smoother
+    (oracle/parsmooth_np.py: associative_scan over sqrt_filtering_operator / sqrt_smoothing_operator)."""
+    import parsmooth_np as O
+    ys = simulate(model, T_sample, seed)
+    tm = O.FunctionalModel(O.lgssm_function(model["F"]), O.MVNSqrt(model["b"], model["cholQ"]))
+    om = O.FunctionalModel(O.lgssm_function(model["H"]), O.MVNSqrt(model["c"], model["cholR"]))
+    x0 = O.MVNSqrt(model["m0"], model["L0"])
+    base, tt = _threaded_tria(threads)
+    O.tria = tt
+    try:
+        t0 = time.perf_counter()
+        O.filter_smoother(ys, x0, tm, om, O.extended, None, True)
+        dt = time.perf_counter() - t0
+    finally:
+        O.tria = base
+    return T_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    model = make_lgssm(NX, NY)
+    T_sample = 100_000
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_pass_rate(model, 10_000, threads)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_pass_rate(model, T_sample, threads)
+        rates.append(r)
+        times.append(dt)
+    value = T_sample * len(times) / sum(times)
+    sample = (f"NumPy restatement of parsmooth's parallel sqrt filter+smoother (associative_scan, batched LAPACK QR "
+              f"split over {threads} threads), T={T_sample} sample of the T=1e6 workload, per-step rate")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C1 LGSSM nx=4 ny=2, one filter_smoother pass; CPU arm times a T=1e5 sample",
+                   "nx": NX, "ny": NY, "T_sample": T_sample},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "JAX/jaxlib are not installed and not in /opt/wheelhouse: the unmodified reference cannot run; "
+                "this arm is the oracle port (see DESIGN.md).",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# psqrt arm
+# --------------------------------------------------------------------------------------------------
+def run_psqrt(args):
+    import torch
+    import torch.distributed as dist
+    import psqrt
+    from psqrt import _lib
+    from psqrt._lib import LinearizedSSM
+    from psqrt.models import lgssm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the psqrt arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    T = args.T
+    model = make_lgssm(NX, NY)
+    ys_np = simulate(model, T, seed=1000 + rank)
+    g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    ssm = LinearizedSSM(*[g(model[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")])
+    ys = g(ys_np)
+    m0, L0 = g(model["m0"]), g(model["L0"])
+    x0 = psqrt.MVNSqrt(m0, L0)
+    tm = psqrt.FunctionalModel(lgssm.transition_function(model["F"]), psqrt.MVNSqrt(g(model["b"]), g(model["cholQ"])))
+    om = psqrt.FunctionalModel(lgssm.observation_function(model["H"]), psqrt.MVNSqrt(g(model["c"]), g(model["cholR"])))
+
+    if world > 1:
+        from psqrt import dist as pdist
+        sharded = pdist.TimeShardedSmoother(NX, NY, T, device=dev)
+
+        def one_pass():
+            return sharded.filter_smoother(ssm, ys[None], m0[None], L0[None])
+    else:
+        def one_pass():
+            return _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = T * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------
+    ys_host = torch.as_tensor(ys_np).pin_memory()
+    out_m = torch.empty((T + 1, NX), dtype=torch.float64).pin_memory()
+    out_L = torch.empty((T + 1, NX, NX), dtype=torch.float64).pin_memory()
+
+    def e2e_pass():
+        y_dev = ys_host.to(dev, non_blocking=True)
+        if world > 1:
+            fm, fL, sm, sL, _ = one_pass_from(y_dev)
+        else:
+            res = psqrt.filter_smoother(y_dev, x0, tm, om, psqrt.linearization.extended, None, True)
+            sm, sL = res.mean, res.chol
+        out_m.copy_(sm.reshape(out_m.shape), non_blocking=True)
+        out_L.copy_(sL.reshape(out_L.shape), non_blocking=True)
+
+    if world > 1:
+        def one_pass_from(y_dev):
+            return sharded.filter_smoother(ssm, y_dev[None], m0[None], L0[None])
+
+    for _ in range(2):
+        e2e_pass()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(3, min(args.steps, 10))
+    e2.record()
+    for _ in range(n_e2e):
+        e2e_pass()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    ms_e2e /= n_e2e
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = {"value": T * world / (ms_e2e * 1e-3), "unit": "steps/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(ys_host.numel() * 8) * world,
+           "d2h_bytes_per_step": int((out_m.numel() + out_L.numel()) * 8) * world}
+
+    # ---- per-kernel-stage timing for the roofline (staged C-ABI calls, same kernels) -------------
+    roofline = None
+    stages = None
+    if rank == 0:
+        yb, m0b, L0b = ys[None].contiguous(), m0[None].contiguous(), L0[None].contiguous()
+        names = ("filter_reduce(K1+K2)", "filter_apply+smooth_reduce(K3+K4)", "smooth_apply(K5)")
+        acc = {n: [] for n in names}
+        for it in range(3 + 10):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            _lib.filter_reduce(ssm, yb, NX)
+            ev[1].record()
+            fm, fL, _, stot = _lib.filter_apply(ssm, yb, m0b, L0b, smooth=True, loglik=False)
+            ev[2].record()
+            _lib.smoother_apply(ssm, fm, fL, fm[:, -1].contiguous(), fL[:, -1].contiguous())
+            ev[3].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                for i, n in enumerate(names):
+                    acc[n].append(ev[i].elapsed_time(ev[i + 1]))
+        stages = {n: float(np.median(v)) for n, v in acc.items()}
+        # canonical per-step bytes attributed to each stage
+        share = {names[0]: 8 * (3 * NX * NX + 2 * NX), names[1]: 8 * (NX * NX + NX),
+                 names[2]: 8 * (2 * NX * NX + NX) + 8 * (NX * NX + NX)}
+        dom = max(stages, key=stages.get)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = share[dom] * T / (stages[dom] * 1e-3) / 1e9
+        pass_achieved = algorithmic_bytes_per_step(NX) * (T / (ms_per_step * 1e-3)) / 1e9 if world == 1 else None
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": share[dom], "stage_ms": stages,
+                    "whole_pass": {"algorithmic_bytes_per_step": algorithmic_bytes_per_step(NX),
+                                   "achieved": pass_achieved, "frac": (pass_achieved / peak) if pass_achieved else None}}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) -----------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_pass_rate(model, 5_000, threads)
+        r, dt = cpu_pass_rate(model, 100_000, threads)
+        cpu_baseline = {"value": r, "unit": "steps/s", "cores": threads, "kind": "port",
+                        "sample": f"NumPy restatement of the reference's parallel sqrt filter+smoother on a T=1e5 "
+                                  f"sample of the same LGSSM ({dt:.1f} s), LAPACK QR batch split over {threads} threads"}
+
+    if rank == 0:
+        plan = _lib.get_plan(NX, NY, T, 1, 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C1 random stable LGSSM nx=4 ny=2, T=1e6 steps per GPU, one sqrt parallel "
+                                   "filter_smoother pass per step" + (", time-sharded over the GPUs with 2 NCCL "
+                                                                      "all-gathers of shard totals" if world > 1 else ""),
+                       "nx": NX, "ny": NY, "T_per_gpu": T, "T_total": T * world, "chunk_len": plan.chunk_len,
+                       "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
+                       "l2": "working set per pass (y 16 MB + filtered 160 MB + smoothed 160 MB) exceeds the 126 MB L2; "
+                             "no explicit flush"},
+            "e2e": e2e, "gpu_launches": (6 if world == 1 else 9) * args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="psqrt", choices=["psqrt", "reference"])
+    ap.add_argument("--T", type=int, default=T_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_psqrt(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,156 @@
+/* psqrt.h -- C ABI of libpsqrt.so: the B200 (sm_100a) square-root parallel Kalman filter /
+ * RTS smoother path of EEA-sensors/sqrt-parallel-smoothers ("parsmooth").
+ *
+ * The reference has no FFI of its own (it is pure Python on JAX); its seams for this path are
+ *   - the API facade                parsmooth/methods.py:14-76
+ *   - the linearization protocol    parsmooth/parallel/_filtering.py:117-119, _smoothing.py:73
+ *   - the associative-scan seam     parsmooth/parallel/_filtering.py:34-35, _smoothing.py:33-34
+ * Each entry point below names the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes binding (used by the PyTorch host layer in this repo) and the XLA-FFI shim a
+ * parsmooth maintainer would add to call the same symbols from JAX.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned, contiguous, 8-byte aligned fp64 data
+ *     (row-major, batch outermost, then time); nothing is allocated or freed by the library;
+ *   - scratch comes from the caller: size it with psqrt_workspace_bytes();
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises the device and never throws;
+ *   - return value: PSQRT_OK or a negative PSQRT_E* code (psqrt_error_string() names it);
+ *   - square-root factors are compared/defined up to a right orthogonal factor, exactly like
+ *     the reference's tria() (parsmooth/_utils.py:22-24): only L L^T is meaningful;
+ *   - trajectories have T+1 entries (index 0 = prior / carry-in state).
+ */
+#ifndef PSQRT_H_
+#define PSQRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSQRT_VERSION 100 /* 0.1.0 */
+
+#define PSQRT_OK 0
+#define PSQRT_EINVAL (-1)       /* null pointer / non-positive size / bad enum            */
+#define PSQRT_EUNSUPPORTED (-2) /* (nx, ny) not in the compiled set (psqrt_supported())   */
+#define PSQRT_EWORKSPACE (-3)   /* workspace too small                                    */
+#define PSQRT_ECUDA (-4)        /* a launch failed (cudaGetLastError() != cudaSuccess)    */
+
+/* op codes for psqrt_workspace_bytes */
+#define PSQRT_OP_FILTER_SMOOTHER 0 /* also covers FILTER, SMOOTHER and the staged calls    */
+#define PSQRT_OP_ELEMENT_SCAN 1    /* psqrt_filter_scan / psqrt_smoother_scan             */
+
+/* Linearised state-space model, what linearization_method(model, nominal) returns for every
+ * step (parsmooth/parallel/_filtering.py:117-119):
+ *     x_{k+1} = F_k x_k + b_k + N(0, cholQ_k cholQ_k^T)        F [nx,nx] cholQ [nx,nx] b [nx]
+ *     y_k     = H_k x_{k+1} + c_k + N(0, cholR_k cholR_k^T)    H [ny,nx] cholR [ny,ny] c [ny]
+ * *_ts is the stride in doubles between consecutive time steps (0 = time-invariant),
+ * *_bs the stride between sequences of a batch (0 = shared).  H, cholR, c may be NULL for
+ * smoother-only calls. */
+typedef struct psqrt_ssm {
+  const double *F, *cholQ, *b, *H, *cholR, *c;
+  int64_t F_ts, cholQ_ts, b_ts, H_ts, cholR_ts, c_ts;
+  int64_t F_bs, cholQ_bs, b_bs, H_bs, cholR_bs, c_bs;
+} psqrt_ssm;
+
+typedef struct psqrt_plan {
+  int32_t chunk_len;     /* K: consecutive steps handled by one thread                    */
+  int64_t n_chunks;      /* P = ceil(T / K)                                               */
+  int64_t n_chunks_pad;  /* P rounded up to the CTA size                                  */
+  int64_t n_warps;       /* n_chunks_pad / 32 (items of the mid-level scan)               */
+  int32_t nf_filter;     /* doubles in one packed filtering element  2 nx^2 + 3 nx        */
+  int32_t nf_smoother;   /* doubles in one packed smoothing element (3 nx^2 + 3 nx) / 2   */
+} psqrt_plan;
+
+int psqrt_version(void);
+const char* psqrt_error_string(int code);
+/* 1 if kernels for (nx, ny) are compiled in; ny = 0 asks about smoother-only support. */
+int psqrt_supported(int nx, int ny);
+/* Chunking used for a problem size; chunk_len = 0 lets the library choose. */
+int psqrt_get_plan(int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqrt_plan* out);
+size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, int chunk_len);
+
+/* ---- whole pass: filtering + smoothing (methods.py:38-47 filter_smoother, parallel=True,
+ *      MVNSqrt inputs; parallel/_filtering.py:13-61 + parallel/_smoothing.py:14-44) ---------
+ * y [B,T,ny]; m0 [B,nx]; L0 [B,nx,nx] LOWER-TRIANGULAR sqrt of the prior covariance;
+ * fm [B,T+1,nx], fL [B,T+1,nx,nx]: filtered trajectory (index 0 = (m0, L0));
+ * sm, sL: smoothed trajectory, same shapes (both NULL = filter only);
+ * ell [B] log-likelihood (NULL = skip; parallel/_filtering.py:53-60). */
+int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m0, const double* L0,
+                          int nx, int ny, int64_t T, int64_t batch, int chunk_len,
+                          double* fm, double* fL, double* sm, double* sL, double* ell,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* smoothing(...) on an existing filtered trajectory (parallel/_smoothing.py:14-57).  fL must
+ * be lower triangular (what psqrt_filter_smoother writes). */
+int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int nx, int64_t T,
+                   int64_t batch, int chunk_len, double* sm, double* sL, void* ws, size_t ws_bytes,
+                   void* stream);
+
+/* ---- staged calls for a time-sharded run (one shard per GPU) --------
+ * 1. psqrt_filter_reduce  : local chunk summaries + shard total  -> ftotal [B, nf_filter]
+ * 2. (all-gather ftotal over ranks)  psqrt_carry_filter: fold totals of ranks < rank into x0
+ * 3. psqrt_filter_apply   : filtered trajectory of the shard from the carry-in state, ell
+ *                           partial; with stotal != NULL also the smoothing reduce -> stotal
+ * 4. (all-gather stotal + last rank's terminal state)  psqrt_carry_smoother
+ * 5. psqrt_smoother_apply : smoothed trajectory of the shard from the carry-in state.
+ * The same workspace must be passed to 1, 3 and 5. */
+int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
+                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, void* stream);
+int psqrt_carry_filter(const double* totals /*[R,B,nf_filter]*/, int rank, int64_t batch, int nx,
+                       const double* m0, const double* L0, double* carry_m, double* carry_L, void* stream);
+int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carry_m, const double* carry_L,
+                       int nx, int ny, int64_t T, int64_t batch, int chunk_len, double* fm, double* fL,
+                       double* ell, double* stotal, void* ws, size_t ws_bytes, void* stream);
+int psqrt_carry_smoother(const double* totals /*[R,B,nf_smoother]*/, int rank, int n_ranks, int64_t batch,
+                         int nx, const double* mT, const double* LT, double* carry_m, double* carry_L,
+                         void* stream);
+int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
+                         const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch,
+                         int chunk_len, double* sm, double* sL, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- element-level seams (for callers that build or consume the associative elements) -----
+ * psqrt_filter_elements   parallel/_filtering.py:100-146  (prior folded into step 0 when m0 != NULL;
+ *                          here L0 may be any dense square-root factor)
+ * psqrt_filter_scan       jax.lax.associative_scan(vmap(sqrt_filtering_operator)) at _filtering.py:34-35:
+ *                          inclusive prefixes, outputs (b, U) = filtered means / factors, [B,T,...]
+ * psqrt_smoother_elements parallel/_smoothing.py:47-57,72-85 (T+1 elements, the last is (m_T, 0, L_T))
+ * psqrt_smoother_scan     reverse associative_scan at _smoothing.py:33-34, outputs (g, D), n = number of elements
+ * psqrt_loglik_terms      parallel/_filtering.py:149-154 per-step terms [B,T] (sum them for ell)
+ * psqrt_filter_combine / psqrt_smoother_combine: one application of
+ *                          parsmooth/parallel/_operators.py:43-77 / 104-125 to n element pairs. */
+int psqrt_filter_elements(const psqrt_ssm* ssm, const double* y, const double* m0, const double* L0,
+                          int nx, int ny, int64_t T, int64_t batch,
+                          double* A, double* b, double* U, double* eta, double* Z, void* stream);
+int psqrt_filter_scan(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                      int nx, int64_t T, int64_t batch, int chunk_len, double* means, double* chols,
+                      void* ws, size_t ws_bytes, void* stream);
+int psqrt_smoother_elements(const psqrt_ssm* ssm, const double* fm, const double* fL, int nx, int64_t T,
+                            int64_t batch, double* g, double* E, double* D, void* stream);
+int psqrt_smoother_scan(const double* g, const double* E, const double* D, int nx, int64_t n, int64_t batch,
+                        int chunk_len, double* means, double* chols, void* ws, size_t ws_bytes, void* stream);
+int psqrt_loglik_terms(const psqrt_ssm* ssm, const double* y, const double* fm, const double* fL,
+                       int nx, int ny, int64_t T, int64_t batch, double* terms, void* stream);
+int psqrt_filter_combine(const double* A1, const double* b1, const double* U1, const double* eta1,
+                         const double* Z1, const double* A2, const double* b2, const double* U2,
+                         const double* eta2, const double* Z2, int nx, int64_t n,
+                         double* A, double* b, double* U, double* eta, double* Z, void* stream);
+int psqrt_smoother_combine(const double* g1, const double* E1, const double* D1, const double* g2,
+                           const double* E2, const double* D2, int nx, int64_t n,
+                           double* g, double* E, double* D, void* stream);
+
+/* ---- math utilities (parsmooth/_utils.py) ------------------------------------------------
+ * psqrt_tria_batched        _utils.py:22-24: A [batch, rows, cols] -> L [batch, rows, rows] lower
+ *                           triangular with L L^T = A A^T (rows <= 8, any cols >= 1)
+ * psqrt_chol_update_batched _utils.py:13-19,39-81: L [batch,n,n] <- chol(L L^T + alpha sum_k v_k v_k^T),
+ *                           V [batch,k,n], sequential over k, non-finite entries -> 0 */
+int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t batch, void* stream);
+int psqrt_chol_update_batched(double* L, const double* V, int n, int k, double alpha, int64_t batch,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSQRT_H_ */

@@ -1,0 +1,109 @@
+"""Build libpsqrt.so (sm_100a) in-tree with nvcc.
+
+    python sqrt-parallel-smoothers_b200/build.py [--force] [--jobs J]
+
+One translation unit per state dimension nx (psqrt_inst.cu with -DPSQ_N=nx) so the fully
+unrolled templates compile in parallel; objects are cached under build/ keyed by the hash of
+the sources and flags.  The result is sqrt-parallel-smoothers_b200/psqrt/libpsqrt.so, which is
+git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+OUT = os.path.join(HERE, "psqrt", "libpsqrt.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NX_LIST = (1, 2, 3, 4, 5, 6, 8)   # compiled state dimensions
+MAX_NY = 4                        # observation dimensions 1..MAX_NY for each of them
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libpsqrt.so cannot be built")
+    return nvcc
+
+
+def _digest(extra: str) -> str:
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(CSRC)):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    with open(os.path.join(INCLUDE, "psqrt.h"), "rb") as f:
+        h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(extra.encode())
+    return h.hexdigest()[:16]
+
+
+def _compile(args):
+    src, obj, defs = args
+    cmd = [_nvcc(), *NVCC_FLAGS, *defs, "-I", INCLUDE, "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    return obj
+
+
+def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    tag = _digest(f"{NX_LIST}{MAX_NY}")
+    stamp = os.path.join(BUILD, "stamp.txt")
+    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == tag:
+        if verbose:
+            print(f"[psqrt build] up to date: {OUT}")
+        return OUT
+    units = []
+    for n in NX_LIST:
+        units.append((os.path.join(CSRC, "psqrt_inst.cu"), os.path.join(BUILD, f"inst_n{n}_{tag}.o"),
+                      [f"-DPSQ_N={n}", f"-DPSQ_MAX_NY={MAX_NY}"]))
+    units.append((os.path.join(CSRC, "psqrt_capi.cu"), os.path.join(BUILD, f"capi_{tag}.o"), []))
+    if os.path.exists(os.path.join(CSRC, "psqrt_models.cu")):
+        units.append((os.path.join(CSRC, "psqrt_models.cu"), os.path.join(BUILD, f"models_{tag}.o"), []))
+    todo = [u for u in units if force or not os.path.exists(u[1])]
+    jobs = jobs or min(len(todo), os.cpu_count() or 1) or 1
+    if verbose:
+        print(f"[psqrt build] compiling {len(todo)} translation units with {jobs} jobs (sm_100a)")
+    # biggest first
+    todo.sort(key=lambda u: -int(u[2][0].split("=")[1]) if u[2] else 0)
+    with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
+        list(ex.map(_compile, todo))
+    objs = [u[1] for u in units]
+    cmd = [_nvcc(), "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed: {r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(tag)
+    # drop stale objects
+    for name in os.listdir(BUILD):
+        if name.endswith(".o") and tag not in name:
+            os.remove(os.path.join(BUILD, name))
+    if verbose:
+        print(f"[psqrt build] wrote {OUT}")
+    return OUT
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    a = ap.parse_args()
+    build(force=a.force, jobs=a.jobs)
+    sys.exit(0)

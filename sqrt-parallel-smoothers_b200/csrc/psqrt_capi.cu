@@ -1,0 +1,368 @@
+// psqrt_capi.cu -- extern "C" entry points declared in include/psqrt.h.
+// Argument checking, chunk planning, workspace carving and dispatch to the per-(nx, ny)
+// launch tables.  No allocation, no synchronisation, no exceptions.
+#include "../../include/psqrt.h"
+
+#include <cuda_runtime.h>
+
+#include "psqrt_kernels.cuh"
+#include "psqrt_launch.h"
+
+namespace {
+
+using psq::LaunchN;
+using psq::LaunchNY;
+using psq::SSMArgs;
+
+const LaunchN* table_for(int nx) {
+  switch (nx) {
+    case 1: return psq::launch_n1();
+    case 2: return psq::launch_n2();
+    case 3: return psq::launch_n3();
+    case 4: return psq::launch_n4();
+    case 5: return psq::launch_n5();
+    case 6: return psq::launch_n6();
+    case 8: return psq::launch_n8();
+    default: return nullptr;
+  }
+}
+
+// Chunking: aim at kTargetThreads resident threads over the whole batch (148 SMs x 256
+// threads, the register-limited occupancy of the sweeps), never fewer than kMinChunk steps per
+// thread so the per-chunk prologue (two applies + one warp scan) stays amortised.
+constexpr long long kTargetThreads = 148LL * 256;
+constexpr int kMinChunk = 4;
+
+int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_plan* p) {
+  if (T <= 0 || batch <= 0 || chunk_len < 0) return PSQRT_EINVAL;
+  long long K = chunk_len;
+  if (K == 0) {
+    long long per_seq = kTargetThreads / batch;
+    if (per_seq < 32) per_seq = 32;
+    K = (T + per_seq - 1) / per_seq;
+    if (K < kMinChunk) K = kMinChunk;
+  }
+  if (K > T) K = T;
+  if (K > 0x7fffffff) return PSQRT_EINVAL;
+  long long P = (T + K - 1) / K;
+  long long Ppad = (P + psq::kBlock - 1) / psq::kBlock * psq::kBlock;
+  p->chunk_len = (int32_t)K;
+  p->n_chunks = P;
+  p->n_chunks_pad = Ppad;
+  p->n_warps = Ppad / 32;
+  p->nf_filter = ln->nf_filter;
+  p->nf_smoother = ln->nf_smoother;
+  return PSQRT_OK;
+}
+
+// Workspace carving (doubles).  One layout serves the fused pass, the staged calls and the
+// element scans, so a workspace sized for the op can be reused across stages.
+struct Ws {
+  double *chunk_pref, *warp_tot, *ftotal, *chunk_suf, *warp_stot, *stotal, *ell_part, *ell_tmp;
+  size_t doubles;
+};
+Ws carve(void* base, const psqrt_plan& p, int64_t B) {
+  Ws w;
+  double* d = (double*)base;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    double* r = d ? d + off : nullptr;
+    off += (n + 1) & ~(size_t)1;  // keep 16-byte alignment
+    return r;
+  };
+  w.chunk_pref = take((size_t)B * p.nf_filter * p.n_chunks_pad);
+  w.warp_tot = take((size_t)B * p.nf_filter * p.n_warps);
+  w.ftotal = take((size_t)B * p.nf_filter);
+  w.chunk_suf = take((size_t)B * p.nf_smoother * p.n_chunks_pad);
+  w.warp_stot = take((size_t)B * p.nf_smoother * p.n_warps);
+  w.stotal = take((size_t)B * p.nf_smoother);
+  w.ell_part = take((size_t)B * p.n_warps);
+  w.ell_tmp = take((size_t)B);
+  w.doubles = off;
+  return w;
+}
+
+SSMArgs make_args(const psqrt_ssm* s, const double* y, int ny, int64_t T) {
+  SSMArgs a;
+  a.F = s->F; a.Q = s->cholQ; a.bq = s->b; a.H = s->H; a.R = s->cholR; a.c = s->c; a.y = y;
+  a.tF = s->F_ts; a.tQ = s->cholQ_ts; a.tb = s->b_ts; a.tH = s->H_ts; a.tR = s->cholR_ts; a.tc = s->c_ts;
+  a.ty = ny;
+  a.sF = s->F_bs; a.sQ = s->cholQ_bs; a.sb = s->b_bs; a.sH = s->H_bs; a.sR = s->cholR_bs; a.sc = s->c_bs;
+  a.sy = (long long)T * ny;
+  return a;
+}
+
+int check_launch() { return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA; }
+
+bool ssm_ok(const psqrt_ssm* s, bool need_obs) {
+  if (!s || !s->F || !s->cholQ || !s->b) return false;
+  if (need_obs && (!s->H || !s->cholR || !s->c)) return false;
+  return true;
+}
+
+struct Ctx {
+  const LaunchN* ln;
+  const LaunchNY* lny;
+  psqrt_plan plan;
+  Ws ws;
+};
+
+int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws, size_t ws_bytes) {
+  c.ln = table_for(nx);
+  if (!c.ln) return PSQRT_EUNSUPPORTED;
+  c.lny = nullptr;
+  if (ny > 0) {
+    c.lny = c.ln->for_ny(ny);
+    if (!c.lny) return PSQRT_EUNSUPPORTED;
+  }
+  if (B > 65535) return PSQRT_EINVAL;
+  int rc = make_plan(c.ln, T, B, chunk_len, &c.plan);
+  if (rc) return rc;
+  c.ws = carve(ws, c.plan, B);
+  if (!ws || ws_bytes < c.ws.doubles * sizeof(double)) return PSQRT_EWORKSPACE;
+  return PSQRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psqrt_version(void) { return PSQRT_VERSION; }
+
+const char* psqrt_error_string(int code) {
+  switch (code) {
+    case PSQRT_OK: return "ok";
+    case PSQRT_EINVAL: return "invalid argument";
+    case PSQRT_EUNSUPPORTED: return "state/observation dimension not compiled in";
+    case PSQRT_EWORKSPACE: return "workspace missing or too small";
+    case PSQRT_ECUDA: return "CUDA launch failed";
+    default: return "unknown error";
+  }
+}
+
+int psqrt_supported(int nx, int ny) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return 0;
+  if (ny == 0) return 1;
+  return ln->for_ny(ny) != nullptr;
+}
+
+int psqrt_get_plan(int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqrt_plan* out) {
+  (void)ny;
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (!out) return PSQRT_EINVAL;
+  return make_plan(ln, T, batch, chunk_len, out);
+}
+
+size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, int chunk_len) {
+  (void)op;
+  (void)ny;
+  const LaunchN* ln = table_for(nx);
+  psqrt_plan p;
+  if (!ln || make_plan(ln, T, batch, chunk_len, &p)) return 0;
+  return carve(nullptr, p, batch).doubles * sizeof(double);
+}
+
+int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
+                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, void* stream) {
+  if (!ssm_ok(ssm, true) || !y || ny <= 0) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SSMArgs a = make_args(ssm, y, ny, T);
+  c.lny->filter_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot, st);
+  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, ftotal ? ftotal : c.ws.ftotal, st);
+  return check_launch();
+}
+
+int psqrt_carry_filter(const double* totals, int rank, int64_t batch, int nx, const double* m0, const double* L0,
+                       double* carry_m, double* carry_L, void* stream) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (rank < 0 || batch <= 0 || !m0 || !L0 || !carry_m || !carry_L || (rank > 0 && !totals)) return PSQRT_EINVAL;
+  ln->carry_filter(totals, rank, batch, m0, L0, carry_m, carry_L, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carry_m, const double* carry_L, int nx,
+                       int ny, int64_t T, int64_t batch, int chunk_len, double* fm, double* fL, double* ell,
+                       double* stotal, void* ws, size_t ws_bytes, void* stream) {
+  if (!ssm_ok(ssm, true) || !y || ny <= 0 || !carry_m || !carry_L || !fm || !fL) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SSMArgs a = make_args(ssm, y, ny, T);
+  const int smooth = stotal != nullptr;
+  c.lny->filter_apply(smooth, a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, c.ws.chunk_pref,
+                      c.ws.warp_tot, fm, fL, c.ws.chunk_suf, c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, st);
+  if (smooth) {
+    c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, stotal, ell ? c.ws.ell_part : nullptr, ell, st);
+  } else if (ell) {
+    psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
+  }
+  return check_launch();
+}
+
+int psqrt_carry_smoother(const double* totals, int rank, int n_ranks, int64_t batch, int nx, const double* mT,
+                         const double* LT, double* carry_m, double* carry_L, void* stream) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (rank < 0 || rank >= n_ranks || batch <= 0 || !mT || !LT || !carry_m || !carry_L ||
+      (rank + 1 < n_ranks && !totals))
+    return PSQRT_EINVAL;
+  ln->carry_smoother(totals, rank, n_ranks, batch, mT, LT, carry_m, carry_L, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
+                         const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
+                         double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
+  if (!ssm_ok(ssm, false) || !fm || !fL || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  SSMArgs a = make_args(ssm, nullptr, 0, T);
+  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, nx, (long long)nx * nx,
+                     c.ws.chunk_suf, c.ws.warp_stot, fm, fL, sm, sL, write_terminal, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m0, const double* L0, int nx, int ny,
+                          int64_t T, int64_t batch, int chunk_len, double* fm, double* fL, double* sm, double* sL,
+                          double* ell, void* ws, size_t ws_bytes, void* stream) {
+  if (!m0 || !L0 || !fm || !fL || ((sm == nullptr) != (sL == nullptr))) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  rc = psqrt_filter_reduce(ssm, y, nx, ny, T, batch, chunk_len, c.ws.ftotal, ws, ws_bytes, stream);
+  if (rc) return rc;
+  const bool smooth = sm != nullptr;
+  rc = psqrt_filter_apply(ssm, y, m0, L0, nx, ny, T, batch, chunk_len, fm, fL, ell, smooth ? c.ws.stotal : nullptr, ws,
+                          ws_bytes, stream);
+  if (rc || !smooth) return rc;
+  // terminal carry = filtered state at index T of every sequence
+  SSMArgs a = make_args(ssm, nullptr, 0, T);
+  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
+                     fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
+                     c.ws.warp_stot, fm, fL, sm, sL, 1, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int nx, int64_t T, int64_t batch,
+                   int chunk_len, double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
+  if (!ssm_ok(ssm, false) || !fm || !fL || !sm || !sL) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  SSMArgs a = make_args(ssm, nullptr, 0, T);
+  c.ln->smooth_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot, st);
+  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.stotal, nullptr, nullptr, st);
+  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
+                     fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
+                     c.ws.warp_stot, fm, fL, sm, sL, 1, st);
+  return check_launch();
+}
+
+int psqrt_filter_elements(const psqrt_ssm* ssm, const double* y, const double* m0, const double* L0, int nx, int ny,
+                          int64_t T, int64_t batch, double* A, double* b, double* U, double* eta, double* Z,
+                          void* stream) {
+  if (!ssm_ok(ssm, true) || !y || T <= 0 || batch <= 0 || !A || !b || !U || !eta || !Z) return PSQRT_EINVAL;
+  if ((m0 == nullptr) != (L0 == nullptr)) return PSQRT_EINVAL;
+  const LaunchN* ln = table_for(nx);
+  const LaunchNY* lny = ln ? ln->for_ny(ny) : nullptr;
+  if (!lny) return PSQRT_EUNSUPPORTED;
+  lny->filter_elements(make_args(ssm, y, ny, T), T, batch, m0, L0, A, b, U, eta, Z, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_filter_scan(const double* A, const double* b, const double* U, const double* eta, const double* Z, int nx,
+                      int64_t T, int64_t batch, int chunk_len, double* means, double* chols, void* ws,
+                      size_t ws_bytes, void* stream) {
+  if (!A || !b || !U || !eta || !Z || !means || !chols) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  c.ln->escan_filter_reduce(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
+                            c.ws.warp_tot, st);
+  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.ftotal, st);
+  c.ln->escan_filter_apply(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
+                           c.ws.warp_tot, means, chols, st);
+  return check_launch();
+}
+
+int psqrt_smoother_elements(const psqrt_ssm* ssm, const double* fm, const double* fL, int nx, int64_t T,
+                            int64_t batch, double* g, double* E, double* D, void* stream) {
+  if (!ssm_ok(ssm, false) || !fm || !fL || T <= 0 || batch <= 0 || !g || !E || !D) return PSQRT_EINVAL;
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  ln->smoother_elements(make_args(ssm, nullptr, 0, T), T, batch, fm, fL, g, E, D, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_smoother_scan(const double* g, const double* E, const double* D, int nx, int64_t n, int64_t batch,
+                        int chunk_len, double* means, double* chols, void* ws, size_t ws_bytes, void* stream) {
+  if (!g || !E || !D || !means || !chols) return PSQRT_EINVAL;
+  Ctx c;
+  int rc = setup(c, nx, 0, n, batch, chunk_len, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  c.ln->escan_smooth_reduce(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
+                            st);
+  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.stotal, nullptr, nullptr, st);
+  c.ln->escan_smooth_apply(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
+                           means, chols, st);
+  return check_launch();
+}
+
+int psqrt_loglik_terms(const psqrt_ssm* ssm, const double* y, const double* fm, const double* fL, int nx, int ny,
+                       int64_t T, int64_t batch, double* terms, void* stream) {
+  if (!ssm_ok(ssm, true) || !y || !fm || !fL || !terms || T <= 0 || batch <= 0) return PSQRT_EINVAL;
+  const LaunchN* ln = table_for(nx);
+  const LaunchNY* lny = ln ? ln->for_ny(ny) : nullptr;
+  if (!lny) return PSQRT_EUNSUPPORTED;
+  lny->loglik_terms(make_args(ssm, y, ny, T), T, batch, fm, fL, terms, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_filter_combine(const double* A1, const double* b1, const double* U1, const double* eta1, const double* Z1,
+                         const double* A2, const double* b2, const double* U2, const double* eta2, const double* Z2,
+                         int nx, int64_t n, double* A, double* b, double* U, double* eta, double* Z, void* stream) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (n <= 0 || !A1 || !b1 || !U1 || !eta1 || !Z1 || !A2 || !b2 || !U2 || !eta2 || !Z2 || !A || !b || !U || !eta || !Z)
+    return PSQRT_EINVAL;
+  ln->filter_combine(A1, b1, U1, eta1, Z1, A2, b2, U2, eta2, Z2, n, A, b, U, eta, Z, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_smoother_combine(const double* g1, const double* E1, const double* D1, const double* g2, const double* E2,
+                           const double* D2, int nx, int64_t n, double* g, double* E, double* D, void* stream) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (n <= 0 || !g1 || !E1 || !D1 || !g2 || !E2 || !D2 || !g || !E || !D) return PSQRT_EINVAL;
+  ln->smooth_combine(g1, E1, D1, g2, E2, D2, n, g, E, D, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t batch, void* stream) {
+  const LaunchN* ln = table_for(rows);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (!A || !L || cols <= 0 || batch <= 0) return PSQRT_EINVAL;
+  ln->tria(A, L, cols, batch, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_chol_update_batched(double* L, const double* V, int n, int k, double alpha, int64_t batch, void* stream) {
+  const LaunchN* ln = table_for(n);
+  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (!L || !V || k < 0 || batch <= 0) return PSQRT_EINVAL;
+  ln->chol_update(L, V, k, alpha, batch, (cudaStream_t)stream);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// psqrt_inst.cu -- instantiates every kernel for ONE state dimension (compile with
+// -DPSQ_N=<nx>); observation dimensions 1..PSQ_MAX_NY are instantiated for that nx.
+#include "psqrt_kernels.cuh"
+#include "psqrt_launch.h"
+
+#ifndef PSQ_N
+#error "compile with -DPSQ_N=<nx>"
+#endif
+#ifndef PSQ_MAX_NY
+#define PSQ_MAX_NY 4
+#endif
+
+namespace psq {
+namespace {
+
+constexpr int N = PSQ_N;
+
+inline dim3 sweep_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kBlock), (unsigned)B, 1); }
+inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+template <int NY>
+struct NYImpl {
+  static void filter_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, double* chunk_pref,
+                            double* warp_tot, cudaStream_t st) {
+    k_filter_reduce<N, NY><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, chunk_pref, warp_tot);
+  }
+  static void filter_apply(int smooth, const SSMArgs& a, long long T, int K, long long Ppad, long long B,
+                           const double* cm, const double* cL, const double* chunk_pref, const double* warp_pref,
+                           double* fm, double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
+                           cudaStream_t st) {
+    if (smooth)
+      k_filter_apply<N, NY, true><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, chunk_pref, warp_pref,
+                                                                        fm, fL, chunk_suf, warp_stot, ell_part);
+    else
+      k_filter_apply<N, NY, false><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, chunk_pref,
+                                                                         warp_pref, fm, fL, chunk_suf, warp_stot,
+                                                                         ell_part);
+  }
+  static void filter_elements(const SSMArgs& a, long long T, long long B, const double* m0, const double* L0,
+                              double* A, double* b, double* U, double* eta, double* Z, cudaStream_t st) {
+    k_filter_elements<N, NY><<<blocks_for(T * B, 128), 128, 0, st>>>(a, T, B, m0, L0, A, b, U, eta, Z);
+  }
+  static void loglik_terms(const SSMArgs& a, long long T, long long B, const double* fm, const double* fL,
+                           double* terms, cudaStream_t st) {
+    k_loglik_terms<N, NY><<<blocks_for(T * B, 128), 128, 0, st>>>(a, T, B, fm, fL, terms);
+  }
+  static const LaunchNY* table() {
+    static const LaunchNY t = {&filter_reduce, &filter_apply, &filter_elements, &loglik_terms};
+    return &t;
+  }
+};
+
+const LaunchNY* for_ny(int ny) {
+  switch (ny) {
+    case 1: return NYImpl<1>::table();
+#if PSQ_MAX_NY >= 2
+    case 2: return NYImpl<2>::table();
+#endif
+#if PSQ_MAX_NY >= 3
+    case 3: return NYImpl<3>::table();
+#endif
+#if PSQ_MAX_NY >= 4
+    case 4: return NYImpl<4>::table();
+#endif
+    default: return nullptr;
+  }
+}
+
+template <class Elem>
+constexpr size_t mid_smem() { return (32 * Elem::NF + 32) * sizeof(double); }
+
+void mid_filter(double* items, long long M, long long B, double* total, cudaStream_t st) {
+  k_mid_scan<FElem<N>, false><<<(unsigned)B, kMidBlock, mid_smem<FElem<N>>(), st>>>(items, M, total, nullptr, nullptr);
+}
+void mid_smooth(double* items, long long M, long long B, double* total, const double* ell_part, double* ell_out,
+                cudaStream_t st) {
+  k_mid_scan<SElem<N>, true><<<(unsigned)B, kMidBlock, mid_smem<SElem<N>>(), st>>>(items, M, total, ell_part, ell_out);
+}
+void smooth_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* fm,
+                   const double* fL, double* chunk_suf, double* warp_stot, cudaStream_t st) {
+  k_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, fm, fL, chunk_suf, warp_stot);
+}
+void smooth_apply(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* cm,
+                  const double* cL, long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
+                  const double* fm, const double* fL, double* sm, double* sL, int write_terminal, cudaStream_t st) {
+  k_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, fm,
+                                                           fL, sm, sL, write_terminal);
+}
+void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
+                  double* cL, cudaStream_t st) {
+  k_carry_filter<N><<<blocks_for(B, 32), 32, 0, st>>>(totals, rank, B, m0, L0, cm, cL);
+}
+void carry_smoother(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
+                    double* cm, double* cL, cudaStream_t st) {
+  k_carry_smoother<N><<<blocks_for(B, 32), 32, 0, st>>>(totals, rank, R, B, mT, LT, cm, cL);
+}
+void smoother_elements(const SSMArgs& a, long long T, long long B, const double* fm, const double* fL, double* g,
+                       double* E, double* D, cudaStream_t st) {
+  k_smoother_elements<N><<<blocks_for((T + 1) * B, 128), 128, 0, st>>>(a, T, B, fm, fL, g, E, D);
+}
+void escan_filter_reduce(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                         long long T, int K, long long Ppad, long long B, double* chunk_pref, double* warp_tot,
+                         cudaStream_t st) {
+  k_escan_filter_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(A, b, U, eta, Z, T, K, Ppad, chunk_pref, warp_tot);
+}
+void escan_filter_apply(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                        long long T, int K, long long Ppad, long long B, const double* chunk_pref,
+                        const double* warp_pref, double* om, double* oL, cudaStream_t st) {
+  k_escan_filter_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(A, b, U, eta, Z, T, K, Ppad, nullptr, nullptr,
+                                                                 chunk_pref, warp_pref, om, oL);
+}
+void escan_smooth_reduce(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                         long long B, double* chunk_suf, double* warp_stot, cudaStream_t st) {
+  k_escan_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(g, E, D, T, K, Ppad, chunk_suf, warp_stot);
+}
+void escan_smooth_apply(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                        long long B, const double* chunk_suf, const double* warp_suf, double* om, double* oL,
+                        cudaStream_t st) {
+  k_escan_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(g, E, D, T, K, Ppad, nullptr, nullptr, chunk_suf,
+                                                                 warp_suf, om, oL);
+}
+void filter_combine(const double* A1, const double* b1, const double* U1, const double* e1, const double* Z1,
+                    const double* A2, const double* b2, const double* U2, const double* e2, const double* Z2,
+                    long long n, double* A, double* b, double* U, double* eta, double* Z, cudaStream_t st) {
+  k_filter_combine_pairs<N><<<blocks_for(n, 64), 64, 0, st>>>(A1, b1, U1, e1, Z1, A2, b2, U2, e2, Z2, n, A, b, U, eta,
+                                                             Z);
+}
+void smooth_combine(const double* g1, const double* E1, const double* D1, const double* g2, const double* E2,
+                    const double* D2, long long n, double* g, double* E, double* D, cudaStream_t st) {
+  k_smooth_combine_pairs<N><<<blocks_for(n, 64), 64, 0, st>>>(g1, E1, D1, g2, E2, D2, n, g, E, D);
+}
+void tria(const double* A, double* L, int cols, long long batch, cudaStream_t st) {
+  k_tria_batched<N><<<blocks_for(batch, 128), 128, 0, st>>>(A, L, cols, batch);
+}
+void chol_update(double* L, const double* V, int k, double alpha, long long batch, cudaStream_t st) {
+  k_chol_update_batched<N><<<blocks_for(batch, 128), 128, 0, st>>>(L, V, k, alpha, batch);
+}
+
+const LaunchN kTable = {N,
+                        FElem<N>::NF,
+                        SElem<N>::NF,
+                        &for_ny,
+                        &mid_filter,
+                        &mid_smooth,
+                        &smooth_reduce,
+                        &smooth_apply,
+                        &carry_filter,
+                        &carry_smoother,
+                        &smoother_elements,
+                        &escan_filter_reduce,
+                        &escan_filter_apply,
+                        &escan_smooth_reduce,
+                        &escan_smooth_apply,
+                        &filter_combine,
+                        &smooth_combine,
+                        &tria,
+                        &chol_update};
+
+}  // namespace
+
+#define PSQ_CAT_(a, b) a##b
+#define PSQ_CAT(a, b) PSQ_CAT_(a, b)
+const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return &kTable; }
+
+#if PSQ_N == 1
+void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
+  k_ell_sum<0><<<(unsigned)B, 256, 0, st>>>(ell_part, M, ell_out);
+}
+#endif
+
+}  // namespace psq

@@ -1,0 +1,730 @@
+// psqrt_kernels.cuh -- the five kernels of one square-root parallel filter + RTS smoother pass.
+//
+// Time is cut into P chunks of K consecutive steps, one chunk per thread, 32 chunks per warp.
+//   K1 filter_reduce   : per chunk, the chunk summary (A,b,U,eta,Z) by the collapsed combine
+//                        (psq::filter_reduce_step); warp-level Kogge-Stone scan of the 32
+//                        summaries (generic combine, parsmooth/parallel/_operators.py:43-77);
+//                        writes the in-warp exclusive prefix per chunk and one total per warp.
+//   K2 mid_scan<FElem> : one CTA per sequence scans the warp totals (exclusive), emits the
+//                        sequence total (the element a time-sharded run all-gathers).
+//   K3 filter_apply    : carry-in state pushed through the two exclusive prefixes, then a
+//                        sequential sqrt Kalman filter inside the chunk; writes filtered
+//                        (mean, chol), accumulates the log-likelihood, and (SMOOTH) builds the
+//                        smoothing elements from the same triangularisation and reduces them.
+//   K4 mid_scan<SElem> : reverse scan of the smoothing warp totals; sums the ell partials.
+//   K5 smooth_apply    : carry-in (terminal) state pushed through the suffixes, then the RTS
+//                        recursion backwards inside the chunk; writes smoothed (mean, chol).
+// The associative-scan seam of the reference (jax.lax.associative_scan at
+// parallel/_filtering.py:34-35 and parallel/_smoothing.py:33-34) is K1..K5 together.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "psqrt_math.cuh"
+
+namespace psq {
+
+constexpr int kBlock = 128;      // threads per CTA in the sweeps (4 warps)
+constexpr int kMidBlock = 256;   // threads of the single mid-scan CTA (255 regs/thread available)
+constexpr unsigned kFull = 0xffffffffu;
+
+// Linearised SSM as the kernels see it: base pointers + per-step and per-sequence strides in
+// doubles (0 = shared by all steps / all sequences).
+struct SSMArgs {
+  const double *F, *Q, *bq, *H, *R, *c, *y;
+  long long tF, tQ, tb, tH, tR, tc, ty;  // time strides
+  long long sF, sQ, sb, sH, sR, sc, sy;  // sequence (batch) strides
+};
+
+__device__ __forceinline__ StepPtrs step_ptrs(const SSMArgs& a, long long seq, long long k) {
+  StepPtrs p;
+  p.F = a.F + seq * a.sF + k * a.tF;
+  p.Q = a.Q + seq * a.sQ + k * a.tQ;
+  p.bq = a.bq + seq * a.sb + k * a.tb;
+  p.H = a.H ? a.H + seq * a.sH + k * a.tH : nullptr;
+  p.R = a.R ? a.R + seq * a.sR + k * a.tR : nullptr;
+  p.c = a.c ? a.c + seq * a.sc + k * a.tc : nullptr;
+  p.y = a.y ? a.y + seq * a.sy + k * a.ty : nullptr;
+  return p;
+}
+
+// ---- element traits: combine(acc, x) with acc = everything earlier in SCAN order ------------
+template <class Elem>
+struct ScanOp;
+template <int N>
+struct ScanOp<FElem<N>> {  // forward in time: acc = earlier = elem1
+  static __device__ __forceinline__ FElem<N> combine(const FElem<N>& acc, const FElem<N>& x) {
+    return filtering_combine<N>(acc, x);
+  }
+};
+template <int N>
+struct ScanOp<SElem<N>> {  // backward in time: acc = later = elem1
+  static __device__ __forceinline__ SElem<N> combine(const SElem<N>& acc, const SElem<N>& x) {
+    return smoothing_combine<N>(acc, x);
+  }
+};
+
+// SoA scratch: field f of item i of sequence seq lives at buf[(seq * NF + f) * n_items + i]
+template <class Elem>
+__device__ __forceinline__ void soa_store(double* buf, long long seq, long long n_items, long long i, const Elem& e) {
+  double* p = buf + seq * Elem::NF * n_items + i;
+#pragma unroll
+  for (int f = 0; f < Elem::NF; ++f) p[f * n_items] = e.v[f];
+}
+template <class Elem>
+__device__ __forceinline__ void soa_load(const double* buf, long long seq, long long n_items, long long i, Elem& e) {
+  const double* p = buf + seq * Elem::NF * n_items + i;
+#pragma unroll
+  for (int f = 0; f < Elem::NF; ++f) e.v[f] = p[f * n_items];
+}
+
+template <class Elem, bool REV>
+__device__ __forceinline__ Elem shfl_elem(const Elem& e, int delta) {
+  Elem o;
+#pragma unroll
+  for (int f = 0; f < Elem::NF; ++f)
+    o.v[f] = REV ? __shfl_down_sync(kFull, e.v[f], delta) : __shfl_up_sync(kFull, e.v[f], delta);
+  return o;
+}
+
+// Inclusive Kogge-Stone scan across the 32 lanes.  REV = false: lane order is scan order;
+// REV = true: lane 31 comes first in scan order (suffix scan).
+template <class Elem, bool REV>
+__device__ __forceinline__ Elem warp_scan_inclusive(Elem e, int lane) {
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Elem o = shfl_elem<Elem, REV>(e, d);
+    const bool valid = REV ? (lane + d < 32) : (lane >= d);
+    Elem c = ScanOp<Elem>::combine(o, e);
+    if (valid) e = c;
+  }
+  return e;
+}
+
+// exclusive = inclusive of the previous lane in scan order (identity for the first lane)
+template <class Elem, bool REV>
+__device__ __forceinline__ Elem warp_exclusive_from_inclusive(const Elem& incl, int lane) {
+  Elem x = shfl_elem<Elem, REV>(incl, 1);
+  const bool first = REV ? (lane == 31) : (lane == 0);
+  if (first) x.set_identity();
+  return x;
+}
+
+template <int N>
+__device__ __forceinline__ void load_gauss_dense(const double* m, const double* L, Gauss<N>& x) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x.m[i] = m[i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) x.Lc(i, j) = L[i * N + j];
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_gauss_dense(double* m, double* L, const Gauss<N>& x) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    m[i] = x.m[i];
+#pragma unroll
+    for (int j = 0; j < N; ++j) L[i * N + j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  }
+}
+
+// =========================================================================================
+// K1
+// =========================================================================================
+template <int N, int NY>
+__global__ void __launch_bounds__(kBlock)
+k_filter_reduce(SSMArgs a, long long T, int K, long long Ppad, double* __restrict__ chunk_pref,
+                double* __restrict__ warp_tot) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  FElem<N> acc;
+  acc.set_identity();
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    StepPtrs p = step_ptrs(a, seq, k);
+    filter_reduce_step<N, NY>(acc, p);
+  }
+  FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(acc, lane);
+  FElem<N> excl = warp_exclusive_from_inclusive<FElem<N>, false>(incl, lane);
+  soa_store(chunk_pref, seq, Ppad, c, excl);
+  if (lane == 31) soa_store(warp_tot, seq, Ppad / 32, c / 32, incl);
+}
+
+// =========================================================================================
+// K2 / K4: exclusive scan of M items by one CTA per sequence (items in place -> exclusive
+// prefixes in scan order; total written to total_out[seq][NF]).  REV mirrors the index.
+// Optionally sums ell partials (deterministic order) into ell_out[seq].
+// =========================================================================================
+template <class Elem, bool REV>
+__global__ void __launch_bounds__(kMidBlock)
+k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ total_out,
+           const double* __restrict__ ell_part, double* __restrict__ ell_out) {
+  extern __shared__ double smem[];  // [32][NF] warp totals, then [32] ell
+  const long long seq = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long q = (M + kMidBlock - 1) / kMidBlock;
+  const long long s0 = (long long)tid * q;
+  const long long s1 = (s0 + q < M) ? s0 + q : M;
+
+  Elem acc;
+  acc.set_identity();
+#pragma unroll 1
+  for (long long s = s0; s < s1; ++s) {
+    Elem x;
+    soa_load(items, seq, M, REV ? (M - 1 - s) : s, x);
+    acc = ScanOp<Elem>::combine(acc, x);
+  }
+  Elem incl = warp_scan_inclusive<Elem, false>(acc, lane);
+  if (lane == 31) {
+#pragma unroll
+    for (int f = 0; f < Elem::NF; ++f) smem[warp * Elem::NF + f] = incl.v[f];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    Elem w;
+    w.set_identity();
+    if (lane < kMidBlock / 32) {
+#pragma unroll
+      for (int f = 0; f < Elem::NF; ++f) w.v[f] = smem[lane * Elem::NF + f];
+    }
+    Elem wi = warp_scan_inclusive<Elem, false>(w, lane);
+    Elem we = warp_exclusive_from_inclusive<Elem, false>(wi, lane);
+    if (lane == 31 && total_out) {
+#pragma unroll
+      for (int f = 0; f < Elem::NF; ++f) total_out[seq * Elem::NF + f] = wi.v[f];
+    }
+#pragma unroll
+    for (int f = 0; f < Elem::NF; ++f) smem[lane * Elem::NF + f] = we.v[f];
+  }
+  __syncthreads();
+  Elem run;
+  {
+    Elem wexcl;
+#pragma unroll
+    for (int f = 0; f < Elem::NF; ++f) wexcl.v[f] = smem[warp * Elem::NF + f];
+    Elem lexcl = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
+    run = ScanOp<Elem>::combine(wexcl, lexcl);
+  }
+#pragma unroll 1
+  for (long long s = s0; s < s1; ++s) {
+    const long long i = REV ? (M - 1 - s) : s;
+    Elem x;
+    soa_load(items, seq, M, i, x);
+    soa_store(items, seq, M, i, run);
+    if (s + 1 < s1) run = ScanOp<Elem>::combine(run, x);
+  }
+  if (ell_part) {  // fixed-order block sum of the per-warp log-likelihood partials
+    double* sred = smem + 32 * Elem::NF;
+    double s = 0.0;
+    for (long long i = tid; i < M; i += kMidBlock) s += ell_part[seq * M + i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(kFull, s, d);
+    __syncthreads();
+    if (lane == 0) sred[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = (lane < kMidBlock / 32) ? sred[lane] : 0.0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(kFull, t, d);
+      if (lane == 0) ell_out[seq] = t;
+    }
+  }
+}
+
+// =========================================================================================
+// K3
+// =========================================================================================
+template <int N, int NY, bool SMOOTH>
+__global__ void __launch_bounds__(kBlock)
+k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
+               const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // [B][N], [B][N][N] lower
+               const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
+               double* __restrict__ fm, double* __restrict__ fL,  // [B][T+1][N], [B][T+1][N][N]; index k+1 written
+               double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+
+  Gauss<N> x;
+  load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
+  {
+    FElem<N> e;
+    soa_load(warp_pref, seq, Mw, c / 32, e);
+    filtering_apply<N>(x, e);
+    soa_load(chunk_pref, seq, Ppad, c, e);
+    filtering_apply<N>(x, e);
+  }
+  double* fmS = fm + seq * (T + 1) * N;
+  double* fLS = fL + seq * (T + 1) * N * N;
+  if (c == 0) store_gauss_dense<N>(fmS, fLS, x);  // trajectory index 0 = carry-in state
+  double ell = 0.0;
+  SElem<N> sacc;
+  sacc.set_identity();
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    StepPtrs p = step_ptrs(a, seq, k);
+    SElem<N> se;
+    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
+    store_gauss_dense<N>(fmS + (k + 1) * N, fLS + (k + 1) * N * N, x);
+    if (SMOOTH) {
+      if (k == k0) sacc = se;
+      else sacc = smoothing_combine<N>(se, sacc);  // se is the later side
+    }
+  }
+  if (ell_part) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
+    if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
+  }
+  if (SMOOTH) {
+    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
+    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+    soa_store(chunk_suf, seq, Ppad, c, excl);
+    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+  }
+}
+
+// Standalone smoothing reduce (smoothing(...) called on an existing filter trajectory).
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __restrict__ fm,
+                const double* __restrict__ fL, double* __restrict__ chunk_suf, double* __restrict__ warp_stot) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  const double* fmS = fm + seq * (T + 1) * N;
+  const double* fLS = fL + seq * (T + 1) * N * N;
+  SElem<N> sacc;
+  sacc.set_identity();
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    StepPtrs p = step_ptrs(a, seq, k);
+    Gauss<N> xf;
+    load_gauss_dense<N>(fmS + k * N, fLS + k * N * N, xf);
+    SElem<N> se;
+    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+    sacc = (k == k0) ? se : smoothing_combine<N>(se, sacc);
+  }
+  SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
+  SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+  soa_store(chunk_suf, seq, Ppad, c, excl);
+  if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+}
+
+// =========================================================================================
+// K5
+// =========================================================================================
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_smooth_apply(SSMArgs a, long long T, int K, long long Ppad,
+               const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // smoothed state at index T
+               long long carry_mstride, long long carry_Lstride,
+               const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
+               const double* __restrict__ fm, const double* __restrict__ fL,
+               double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  if (k0 >= k1) return;  // no warp-level communication below this point
+  Gauss<N> xs;
+  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
+  double* smS = sm + seq * (T + 1) * N;
+  double* sLS = sL + seq * (T + 1) * N * N;
+  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
+  {
+    SElem<N> e;
+    soa_load(warp_suf, seq, Mw, c / 32, e);
+    smoothing_apply<N>(xs, e);
+    soa_load(chunk_suf, seq, Ppad, c, e);
+    smoothing_apply<N>(xs, e);
+  }
+  const double* fmS = fm + seq * (T + 1) * N;
+  const double* fLS = fL + seq * (T + 1) * N * N;
+#pragma unroll 1
+  for (long long k = k1 - 1; k >= k0; --k) {
+    StepPtrs p = step_ptrs(a, seq, k);
+    Gauss<N> xf;
+    load_gauss_dense<N>(fmS + k * N, fLS + k * N * N, xf);
+    SElem<N> se;
+    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+    smoothing_apply<N>(xs, se);
+    store_gauss_dense<N>(smS + k * N, sLS + k * N * N, xs);
+  }
+}
+
+// =========================================================================================
+// Time-shard carries (multi-GPU): fold the all-gathered shard totals of the ranks before
+// (filter) / after (smoother) this one into the carry-in state.  One thread per sequence.
+// =========================================================================================
+template <int N>
+__global__ void k_carry_filter(const double* __restrict__ totals /*[R][B][NF]*/, int rank, long long B,
+                               const double* __restrict__ m0, const double* __restrict__ L0,
+                               double* __restrict__ cm, double* __restrict__ cL) {
+  const long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= B) return;
+  Gauss<N> x;
+  load_gauss_dense<N>(m0 + seq * N, L0 + seq * N * N, x);
+#pragma unroll 1
+  for (int r = 0; r < rank; ++r) {
+    FElem<N> e;
+    const double* p = totals + ((long long)r * B + seq) * FElem<N>::NF;
+#pragma unroll
+    for (int f = 0; f < FElem<N>::NF; ++f) e.v[f] = p[f];
+    filtering_apply<N>(x, e);
+  }
+  store_gauss_dense<N>(cm + seq * N, cL + seq * N * N, x);
+}
+
+template <int N>
+__global__ void k_carry_smoother(const double* __restrict__ totals /*[R][B][NF]*/, int rank, int R, long long B,
+                                 const double* __restrict__ mT, const double* __restrict__ LT,
+                                 double* __restrict__ cm, double* __restrict__ cL) {
+  const long long seq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= B) return;
+  Gauss<N> x;
+  load_gauss_dense<N>(mT + seq * N, LT + seq * N * N, x);
+#pragma unroll 1
+  for (int r = R - 1; r > rank; --r) {
+    SElem<N> e;
+    const double* p = totals + ((long long)r * B + seq) * SElem<N>::NF;
+#pragma unroll
+    for (int f = 0; f < SElem<N>::NF; ++f) e.v[f] = p[f];
+    smoothing_apply<N>(x, e);
+  }
+  store_gauss_dense<N>(cm + seq * N, cL + seq * N * N, x);
+}
+
+// =========================================================================================
+// Element-level kernels (the reference's own seams, one thread per time step)
+// =========================================================================================
+template <int N, int NY>
+__global__ void k_filter_elements(SSMArgs a, long long T, long long B, const double* __restrict__ m0,
+                                  const double* __restrict__ L0, double* __restrict__ A, double* __restrict__ b,
+                                  double* __restrict__ U, double* __restrict__ eta, double* __restrict__ Z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * B) return;
+  const long long seq = i / T, k = i % T;
+  StepPtrs p = step_ptrs(a, seq, k);
+  const bool first = (k == 0) && m0 != nullptr;
+  filtering_element<N, NY>(p, first ? m0 + seq * N : nullptr, first ? L0 + seq * N * N : nullptr,
+                           A + i * N * N, b + i * N, U + i * N * N, eta + i * N, Z + i * N * N);
+}
+
+template <int N>
+__global__ void k_smoother_elements(SSMArgs a, long long T, long long B, const double* __restrict__ fm,
+                                    const double* __restrict__ fL, double* __restrict__ g, double* __restrict__ E,
+                                    double* __restrict__ D) {
+  // T+1 elements per sequence; the last one is (m_T, 0, L_T)               _smoothing.py:56-57
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (T + 1) * B) return;
+  const long long seq = i / (T + 1), k = i % (T + 1);
+  Gauss<N> xf;
+  load_gauss_dense<N>(fm + i * N, fL + i * N * N, xf);
+  SElem<N> se;
+  if (k < T) {
+    StepPtrs p = step_ptrs(a, seq, k);
+    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      se.g(r) = xf.m[r];
+#pragma unroll
+      for (int q = 0; q < N; ++q) se.E(r, q) = 0.0;
+#pragma unroll
+      for (int q = 0; q <= r; ++q) se.D(r, q) = xf.Lc(r, q);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    g[i * N + r] = se.g(r);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      E[i * N * N + r * N + q] = se.E(r, q);
+      D[i * N * N + r * N + q] = (q <= r) ? se.D(r, q) : 0.0;
+    }
+  }
+}
+
+template <int N, int NY>
+__global__ void k_loglik_terms(SSMArgs a, long long T, long long B, const double* __restrict__ fm,
+                               const double* __restrict__ fL, double* __restrict__ terms) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * B) return;
+  const long long seq = i / T, k = i % T;
+  StepPtrs p = step_ptrs(a, seq, k);
+  const long long j = seq * (T + 1) + k;  // filtered state at k (i.e. before step k)
+  terms[i] = loglik_term<N, NY>(p, fm + j * N, fL + j * N * N);
+}
+
+// Generic element scans: inputs are reference-layout dense arrays (AoS per step).
+template <int N>
+__device__ __forceinline__ void load_felem_dense(const double* A, const double* b, const double* U, const double* eta,
+                                                 const double* Z, long long i, FElem<N>& e) {
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    e.b(r) = b[i * N + r];
+    e.eta(r) = eta[i * N + r];
+#pragma unroll
+    for (int q = 0; q < N; ++q) e.A(r, q) = A[i * N * N + r * N + q];
+#pragma unroll
+    for (int q = 0; q <= r; ++q) {
+      e.U(r, q) = U[i * N * N + r * N + q];
+      e.Z(r, q) = Z[i * N * N + r * N + q];
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_selem_dense(const double* g, const double* E, const double* D, long long i,
+                                                 SElem<N>& e) {
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    e.g(r) = g[i * N + r];
+#pragma unroll
+    for (int q = 0; q < N; ++q) e.E(r, q) = E[i * N * N + r * N + q];
+#pragma unroll
+    for (int q = 0; q <= r; ++q) e.D(r, q) = D[i * N * N + r * N + q];
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_escan_filter_reduce(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                      long long T, int K, long long Ppad, double* chunk_pref, double* warp_tot) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
+  FElem<N> acc;
+  acc.set_identity();
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    FElem<N> e;
+    load_felem_dense<N>(A, b, U, eta, Z, seq * T + k, e);
+    if (k == k0) acc = e; else acc = filtering_combine<N>(acc, e);
+  }
+  FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(acc, lane);
+  FElem<N> excl = warp_exclusive_from_inclusive<FElem<N>, false>(incl, lane);
+  soa_store(chunk_pref, seq, Ppad, c, excl);
+  if (lane == 31) soa_store(warp_tot, seq, Ppad / 32, c / 32, incl);
+}
+
+// has_carry = 0: plain inclusive scan of the given elements (outputs (b, U) of each prefix).
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_escan_filter_apply(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                     long long T, int K, long long Ppad, const double* carry_m, const double* carry_L,
+                     const double* chunk_pref, const double* warp_pref, double* om, double* oL) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
+  if (k0 >= k1) return;
+  Gauss<N> x;
+  if (carry_m) {
+    load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      x.m[r] = 0.0;
+#pragma unroll
+      for (int q = 0; q <= r; ++q) x.Lc(r, q) = 0.0;
+    }
+  }
+  FElem<N> e;
+  soa_load(warp_pref, seq, Ppad / 32, c / 32, e);
+  filtering_apply<N>(x, e);
+  soa_load(chunk_pref, seq, Ppad, c, e);
+  filtering_apply<N>(x, e);
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    load_felem_dense<N>(A, b, U, eta, Z, seq * T + k, e);
+    filtering_apply<N>(x, e);
+    store_gauss_dense<N>(om + (seq * T + k) * N, oL + (seq * T + k) * N * N, x);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_escan_smooth_reduce(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                      double* chunk_suf, double* warp_stot) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
+  SElem<N> acc;
+  acc.set_identity();
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    SElem<N> e;
+    load_selem_dense<N>(g, E, D, seq * T + k, e);
+    if (k == k0) acc = e; else acc = smoothing_combine<N>(e, acc);
+  }
+  SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(acc, lane);
+  SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+  soa_store(chunk_suf, seq, Ppad, c, excl);
+  if (lane == 0) soa_store(warp_stot, seq, Ppad / 32, c / 32, incl);
+}
+
+// Suffix scan outputs (g, D).  Without a carry the last element seeds the state exactly
+// (g_T, D_T), as the reference's inclusive reverse scan does.
+template <int N>
+__global__ void __launch_bounds__(kBlock)
+k_escan_smooth_apply(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                     const double* carry_m, const double* carry_L, const double* chunk_suf, const double* warp_suf,
+                     double* om, double* oL) {
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
+  if (k0 >= k1) return;
+  Gauss<N> x;
+  if (carry_m) {
+    load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
+  } else {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      x.m[r] = 0.0;
+#pragma unroll
+      for (int q = 0; q <= r; ++q) x.Lc(r, q) = 0.0;
+    }
+  }
+  SElem<N> e;
+  soa_load(warp_suf, seq, Ppad / 32, c / 32, e);
+  smoothing_apply<N>(x, e);
+  soa_load(chunk_suf, seq, Ppad, c, e);
+  smoothing_apply<N>(x, e);
+#pragma unroll 1
+  for (long long k = k1 - 1; k >= k0; --k) {
+    load_selem_dense<N>(g, E, D, seq * T + k, e);
+    smoothing_apply<N>(x, e);
+    store_gauss_dense<N>(om + (seq * T + k) * N, oL + (seq * T + k) * N * N, x);
+  }
+}
+
+// One-off combines of explicit element pairs (unit-test seam for _operators.py).
+template <int N>
+__global__ void k_filter_combine_pairs(const double* A1, const double* b1, const double* U1, const double* e1,
+                                       const double* Z1, const double* A2, const double* b2, const double* U2,
+                                       const double* e2, const double* Z2, long long n, double* A, double* b, double* U,
+                                       double* eta, double* Z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FElem<N> x, y;
+  load_felem_dense<N>(A1, b1, U1, e1, Z1, i, x);
+  load_felem_dense<N>(A2, b2, U2, e2, Z2, i, y);
+  FElem<N> o = filtering_combine<N>(x, y);
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    b[i * N + r] = o.b(r);
+    eta[i * N + r] = o.eta(r);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      A[i * N * N + r * N + q] = o.A(r, q);
+      U[i * N * N + r * N + q] = (q <= r) ? o.U(r, q) : 0.0;
+      Z[i * N * N + r * N + q] = (q <= r) ? o.Z(r, q) : 0.0;
+    }
+  }
+}
+
+template <int N>
+__global__ void k_smooth_combine_pairs(const double* g1, const double* E1, const double* D1, const double* g2,
+                                       const double* E2, const double* D2, long long n, double* g, double* E,
+                                       double* D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SElem<N> x, y;
+  load_selem_dense<N>(g1, E1, D1, i, x);
+  load_selem_dense<N>(g2, E2, D2, i, y);
+  SElem<N> o = smoothing_combine<N>(x, y);
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    g[i * N + r] = o.g(r);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      E[i * N * N + r * N + q] = o.E(r, q);
+      D[i * N * N + r * N + q] = (q <= r) ? o.D(r, q) : 0.0;
+    }
+  }
+}
+
+// Fixed-order sum of per-warp log-likelihood partials (filter-only passes; one CTA / sequence).
+template <int UNUSED>
+__global__ void __launch_bounds__(256)
+k_ell_sum(const double* __restrict__ ell_part, long long M, double* __restrict__ ell_out) {
+  __shared__ double sred[8];
+  const long long seq = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double s = 0.0;
+  for (long long i = tid; i < M; i += 256) s += ell_part[seq * M + i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(kFull, s, d);
+  if (lane == 0) sred[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = (lane < 8) ? sred[lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(kFull, t, d);
+    if (lane == 0) ell_out[seq] = t;
+  }
+}
+
+// tria of a [R x C] matrix per thread, streaming over the columns in blocks of 4:
+// L <- tria([L | next 4 columns]) keeps only R(R+1)/2 + 4R doubles live.   _utils.py:22-24
+template <int R>
+__global__ void k_tria_batched(const double* __restrict__ A, double* __restrict__ L, int C, long long batch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const double* a = A + i * R * C;
+  double Lt[R][R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int q = 0; q < R; ++q) Lt[r][q] = 0.0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    double W[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) W[r][q] = (c0 + q < C) ? a[r * C + c0 + q] : 0.0;
+    tria_append<R, 4>([&](int r, int q) -> double& { return Lt[r][q]; }, W);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int q = 0; q < R; ++q) L[i * R * R + r * R + q] = (q <= r) ? Lt[r][q] : 0.0;
+}
+
+template <int N>
+__global__ void k_chol_update_batched(double* __restrict__ L, const double* __restrict__ V, int k, double alpha,
+                                      long long batch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  double Lt[N][N], w[N];
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int q = 0; q < N; ++q) Lt[r][q] = L[i * N * N + r * N + q];
+#pragma unroll 1
+  for (int v = 0; v < k; ++v) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) w[r] = V[(i * k + v) * N + r];
+    chol_update<N>(Lt, w, alpha);
+  }
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int q = 0; q < N; ++q) L[i * N * N + r * N + q] = Lt[r][q];
+}
+
+}  // namespace psq

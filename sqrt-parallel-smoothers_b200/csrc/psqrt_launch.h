@@ -1,0 +1,73 @@
+// psqrt_launch.h -- type-erased launch tables: one LaunchN per compiled state dimension,
+// one LaunchNY per compiled (nx, ny) pair.  psqrt_inst.cu fills them (one translation unit per
+// nx so the unrolled templates compile in parallel); psqrt_capi.cu dispatches through them.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace psq {
+
+struct SSMArgs;
+
+struct LaunchNY {
+  void (*filter_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, double* chunk_pref,
+                        double* warp_tot, cudaStream_t);
+  void (*filter_apply)(int smooth, const SSMArgs&, long long T, int K, long long Ppad, long long B,
+                       const double* carry_m, const double* carry_L, const double* chunk_pref,
+                       const double* warp_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
+                       double* ell_part, cudaStream_t);
+  void (*filter_elements)(const SSMArgs&, long long T, long long B, const double* m0, const double* L0, double* A,
+                          double* b, double* U, double* eta, double* Z, cudaStream_t);
+  void (*loglik_terms)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* terms,
+                       cudaStream_t);
+};
+
+struct LaunchN {
+  int n;
+  int nf_filter, nf_smoother;
+  const LaunchNY* (*for_ny)(int ny);
+  void (*mid_filter)(double* items, long long M, long long B, double* total, cudaStream_t);
+  void (*mid_smooth)(double* items, long long M, long long B, double* total, const double* ell_part,
+                     double* ell_out, cudaStream_t);
+  void (*smooth_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* fm,
+                        const double* fL, double* chunk_suf, double* warp_stot, cudaStream_t);
+  void (*smooth_apply)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* carry_m,
+                       const double* carry_L, long long cms, long long cLs, const double* chunk_suf,
+                       const double* warp_suf, const double* fm, const double* fL, double* sm, double* sL,
+                       int write_terminal, cudaStream_t);
+  void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
+                       double* cL, cudaStream_t);
+  void (*carry_smoother)(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
+                         double* cm, double* cL, cudaStream_t);
+  void (*smoother_elements)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* g,
+                            double* E, double* D, cudaStream_t);
+  void (*escan_filter_reduce)(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                              long long T, int K, long long Ppad, long long B, double* chunk_pref, double* warp_tot,
+                              cudaStream_t);
+  void (*escan_filter_apply)(const double* A, const double* b, const double* U, const double* eta, const double* Z,
+                             long long T, int K, long long Ppad, long long B, const double* chunk_pref,
+                             const double* warp_pref, double* om, double* oL, cudaStream_t);
+  void (*escan_smooth_reduce)(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                              long long B, double* chunk_suf, double* warp_stot, cudaStream_t);
+  void (*escan_smooth_apply)(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
+                             long long B, const double* chunk_suf, const double* warp_suf, double* om, double* oL,
+                             cudaStream_t);
+  void (*filter_combine)(const double* A1, const double* b1, const double* U1, const double* e1, const double* Z1,
+                         const double* A2, const double* b2, const double* U2, const double* e2, const double* Z2,
+                         long long n, double* A, double* b, double* U, double* eta, double* Z, cudaStream_t);
+  void (*smooth_combine)(const double* g1, const double* E1, const double* D1, const double* g2, const double* E2,
+                         const double* D2, long long n, double* g, double* E, double* D, cudaStream_t);
+  void (*tria)(const double* A, double* L, int cols, long long batch, cudaStream_t);
+  void (*chol_update)(double* L, const double* V, int k, double alpha, long long batch, cudaStream_t);
+};
+
+// defined by the per-nx translation units (psqrt_inst.cu compiled with -DPSQ_N=<nx>)
+const LaunchN* launch_n1();
+const LaunchN* launch_n2();
+const LaunchN* launch_n3();
+const LaunchN* launch_n4();
+const LaunchN* launch_n5();
+const LaunchN* launch_n6();
+const LaunchN* launch_n8();
+void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t);
+
+}  // namespace psq

@@ -1,0 +1,933 @@
+// psqrt_math.cuh -- register-resident fp64 small-matrix algebra for the square-root
+// parallel Kalman filter / RTS smoother (sm_100a).  Everything here is a per-thread,
+// fully unrolled template on the state dimension N and observation dimension NY so that
+// every matrix entry lives in a register (no local arrays survive unrolling).
+//
+// The functions are __host__ __device__ so the very same arithmetic can be exercised by the
+// CPU-only unit tests (tests/hostcheck) where no GPU exists; the product only ever calls
+// them from the CUDA kernels in psqrt_kernels.cuh.
+//
+// Reference formulas (EEA-sensors/sqrt-parallel-smoothers):
+//   tria                     parsmooth/_utils.py:22-24
+//   filtering element        parsmooth/parallel/_filtering.py:115-146
+//   filtering combine        parsmooth/parallel/_operators.py:43-77
+//   smoothing element        parsmooth/parallel/_smoothing.py:72-85
+//   smoothing combine        parsmooth/parallel/_operators.py:104-125
+//   log-likelihood term      parsmooth/parallel/_filtering.py:149-154, _utils.py:152-160
+//   rank-1 Cholesky update   parsmooth/_utils.py:39-81
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PSQ_HD __host__ __device__ __forceinline__
+#define PSQ_UNROLL _Pragma("unroll")
+#else
+#define PSQ_HD inline __attribute__((always_inline))
+#define PSQ_UNROLL
+#endif
+
+namespace psq {
+
+constexpr double kHalfLog2Pi = 0.91893853320467274178;  // log(2*pi)/2
+
+PSQ_HD double ldg(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// Element containers (packed; lower-triangular factors keep only i >= j).
+// ---------------------------------------------------------------------------------------
+template <int N>
+struct FElem {  // filtering element (A, b, U, eta, Z)      _operators.py:58-59
+  static constexpr int TRI = N * (N + 1) / 2;
+  static constexpr int NF = N * N + 2 * N + 2 * TRI;
+  double v[NF];
+  PSQ_HD double& A(int i, int j) { return v[i * N + j]; }
+  PSQ_HD double& b(int i) { return v[N * N + i]; }
+  PSQ_HD double& U(int i, int j) { return v[N * N + N + i * (i + 1) / 2 + j]; }
+  PSQ_HD double& eta(int i) { return v[N * N + N + TRI + i]; }
+  PSQ_HD double& Z(int i, int j) { return v[N * N + 2 * N + TRI + i * (i + 1) / 2 + j]; }
+  PSQ_HD double A(int i, int j) const { return v[i * N + j]; }
+  PSQ_HD double b(int i) const { return v[N * N + i]; }
+  PSQ_HD double U(int i, int j) const { return v[N * N + N + i * (i + 1) / 2 + j]; }
+  PSQ_HD double eta(int i) const { return v[N * N + N + TRI + i]; }
+  PSQ_HD double Z(int i, int j) const { return v[N * N + 2 * N + TRI + i * (i + 1) / 2 + j]; }
+  // identity of the filtering operator: (I, 0, 0, 0, 0)
+  PSQ_HD void set_identity() {
+    PSQ_UNROLL
+    for (int f = 0; f < NF; ++f) v[f] = 0.0;
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) A(i, i) = 1.0;
+  }
+};
+
+template <int N>
+struct SElem {  // smoothing element (g, E, D)               _operators.py:118-119
+  static constexpr int TRI = N * (N + 1) / 2;
+  static constexpr int NF = N + N * N + TRI;
+  double v[NF];
+  PSQ_HD double& g(int i) { return v[i]; }
+  PSQ_HD double& E(int i, int j) { return v[N + i * N + j]; }
+  PSQ_HD double& D(int i, int j) { return v[N + N * N + i * (i + 1) / 2 + j]; }
+  PSQ_HD double g(int i) const { return v[i]; }
+  PSQ_HD double E(int i, int j) const { return v[N + i * N + j]; }
+  PSQ_HD double D(int i, int j) const { return v[N + N * N + i * (i + 1) / 2 + j]; }
+  // identity of the smoothing operator: (0, I, 0)
+  PSQ_HD void set_identity() {
+    PSQ_UNROLL
+    for (int f = 0; f < NF; ++f) v[f] = 0.0;
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) E(i, i) = 1.0;
+  }
+};
+
+template <int N>
+struct Gauss {  // (mean, lower-triangular sqrt factor)
+  static constexpr int TRI = N * (N + 1) / 2;
+  double m[N];
+  double L[TRI];
+  PSQ_HD double& Lc(int i, int j) { return L[i * (i + 1) / 2 + j]; }
+  PSQ_HD double Lc(int i, int j) const { return L[i * (i + 1) / 2 + j]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// tria: Householder reflections from the right (LAPACK dgeqr2 on the transpose).
+// Rows [0, NREFL) of M (R x C) become lower-trapezoidal; the reflectors are applied to every
+// row below.  After the call M[i][j], j <= i, holds the factor; entries right of the
+// diagonal in rows < NREFL are scratch.  A zero tail gives tau = 0 like dlarfg.
+// TRIBLK > 0 declares that row r has no non-zeros right of column TRIBLK + r (the second
+// block is itself lower triangular), which shortens every reflector.
+// ---------------------------------------------------------------------------------------
+template <int R, int C, int NREFL, int TRIBLK = 0>
+PSQ_HD void house_rows(double (&M)[R][C]) {
+  PSQ_UNROLL
+  for (int j = 0; j < NREFL; ++j) {
+    const int kend = (TRIBLK > 0) ? ((TRIBLK + j + 1 < C) ? TRIBLK + j + 1 : C) : C;
+    if (j + 1 >= kend) continue;
+    const double alpha = M[j][j];
+    double sigma = 0.0;
+    PSQ_UNROLL
+    for (int k = j + 1; k < kend; ++k) sigma = fma(M[j][k], M[j][k], sigma);
+    const bool live = sigma != 0.0;
+    const double norm = sqrt(fma(alpha, alpha, sigma));
+    const double beta = live ? -copysign(norm, alpha) : alpha;
+    const double v0 = alpha - beta;  // = alpha + sign(alpha) * norm : no cancellation
+    const double s = live ? 1.0 / (norm * (norm + fabs(alpha))) : 0.0;
+    PSQ_UNROLL
+    for (int i = j + 1; i < R; ++i) {
+      double d = M[i][j] * v0;
+      PSQ_UNROLL
+      for (int k = j + 1; k < kend; ++k) d = fma(M[i][k], M[j][k], d);
+      d *= s;
+      M[i][j] = fma(-d, v0, M[i][j]);
+      PSQ_UNROLL
+      for (int k = j + 1; k < kend; ++k) M[i][k] = fma(-d, M[j][k], M[i][k]);
+    }
+    M[j][j] = beta;
+  }
+}
+
+// Rank-K "update" tria([L | W]) with L (N x N) already lower triangular: row j's reflector
+// touches only column j of L and the K columns of W.
+template <int N, int K, class LAcc>
+PSQ_HD void tria_append(LAcc&& Lij, double (&W)[N][K]) {
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j) {
+    const double alpha = Lij(j, j);
+    double sigma = 0.0;
+    PSQ_UNROLL
+    for (int k = 0; k < K; ++k) sigma = fma(W[j][k], W[j][k], sigma);
+    const bool live = sigma != 0.0;
+    const double norm = sqrt(fma(alpha, alpha, sigma));
+    const double beta = live ? -copysign(norm, alpha) : alpha;
+    const double v0 = alpha - beta;
+    const double s = live ? 1.0 / (norm * (norm + fabs(alpha))) : 0.0;
+    PSQ_UNROLL
+    for (int i = j + 1; i < N; ++i) {
+      double d = Lij(i, j) * v0;
+      PSQ_UNROLL
+      for (int k = 0; k < K; ++k) d = fma(W[i][k], W[j][k], d);
+      d *= s;
+      Lij(i, j) = fma(-d, v0, Lij(i, j));
+      PSQ_UNROLL
+      for (int k = 0; k < K; ++k) W[i][k] = fma(-d, W[j][k], W[i][k]);
+    }
+    Lij(j, j) = beta;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Linearised state-space model of one time step (all row-major, read through the
+// read-only path; a stride of 0 upstream makes every thread read the same address).
+//   x_{k+1} = F x_k + bq + N(0, Q Q^T),   y_k = H x_{k+1} + c + N(0, R R^T)
+// ---------------------------------------------------------------------------------------
+struct StepPtrs {
+  const double* F;   // [N][N]
+  const double* Q;   // [N][N]   any square-root factor of the process noise
+  const double* bq;  // [N]
+  const double* H;   // [NY][N]
+  const double* R;   // [NY][NY] any square-root factor of the observation noise
+  const double* c;   // [NY]
+  const double* y;   // [NY]
+};
+
+// Shared by the Kalman update of both sweeps: given the predicted factor Np (lower, N x N,
+// read through Npij) build Psi = tria([[H Np, R], [Np, 0]])            _filtering.py:126-131
+// On return M2 holds Psi11 (rows/cols < NY), Psi21 (rows >= NY, cols < NY) and the posterior
+// factor (rows >= NY, cols >= NY, lower).
+template <int N, int NY, class NAcc>
+PSQ_HD void build_update(const StepPtrs& p, NAcc&& Npij, double (&M2)[NY + N][N + NY]) {
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double h[N];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double acc = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) acc = fma(h[k], Npij(k, j), acc);
+      M2[a][j] = acc;
+    }
+    PSQ_UNROLL
+    for (int q = 0; q < NY; ++q) M2[a][N + q] = ldg(p.R + a * NY + q);
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    PSQ_UNROLL
+    for (int j = 0; j < N + NY; ++j) M2[NY + i][j] = (j <= i) ? Npij(i, j) : 0.0;
+  }
+  house_rows<NY + N, N + NY, NY + N - 1>(M2);
+}
+
+// Inverse diagonal of Psi11 (NY divisions shared by all forward substitutions).
+template <int N, int NY>
+PSQ_HD void psi11_inv_diag(const double (&M2)[NY + N][N + NY], double (&inv)[NY]) {
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) inv[a] = 1.0 / M2[a][a];
+}
+
+// ---------------------------------------------------------------------------------------
+// Sweep 1 -- chunk-summary recursion.  acc <- acc (x) e_k where e_k is the zero-prior
+// filtering element of step k (_filtering.py:115-146 with m0 = 0, L0 = 0), evaluated without
+// ever forming e_k: the combine _operators.py:58-77 collapses, for a rank-NY information
+// factor Z_k, to one square-root Kalman predict+update on (b, U), two N x N products on A and
+// a rank-NY append on Z.  (Equality with the generic combine is tested against the oracle.)
+// ---------------------------------------------------------------------------------------
+template <int N, int NY>
+PSQ_HD void filter_reduce_step(FElem<N>& acc, const StepPtrs& p) {
+  double F[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+
+  double mp[N], FA[N][N], M1[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = ldg(p.bq + i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], acc.b(k), s);
+    mp[i] = s;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double a = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) a = fma(F[i][k], acc.A(k, j), a);
+      FA[i][j] = a;
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) u = fma(F[i][k], acc.U(k, j), u);
+      M1[i][j] = u;
+      M1[i][N + j] = ldg(p.Q + i * N + j);
+    }
+  }
+  house_rows<N, 2 * N, N>(M1);  // predicted factor = tria([F U | Q])
+
+  double M2[NY + N][N + NY];
+  build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
+  double inv[NY];
+  psi11_inv_diag<N, NY>(M2, inv);
+
+  // V = Psi11^{-1} (H F A)  (NY x N),  rr = Psi11^{-1} (y - H mp - c)
+  double V[NY][N], rr[NY];
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double h[N];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
+    double r = ldg(p.y + a) - ldg(p.c + a);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) r = fma(-h[k], mp[k], r);
+    PSQ_UNROLL
+    for (int q = 0; q < a; ++q) r = fma(-M2[a][q], rr[q], r);
+    rr[a] = r * inv[a];
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(h[k], FA[k][j], s);
+      PSQ_UNROLL
+      for (int q = 0; q < a; ++q) s = fma(-M2[a][q], V[q][j], s);
+      V[a][j] = s * inv[a];
+    }
+  }
+  // A <- FA - Psi21 V ; b <- mp + Psi21 rr ; eta <- eta + V^T rr ; U <- posterior factor
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double bi = mp[i];
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) bi = fma(M2[NY + i][a], rr[a], bi);
+    acc.b(i) = bi;
+    double e = acc.eta(i);
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) e = fma(V[a][i], rr[a], e);
+    acc.eta(i) = e;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = FA[i][j];
+      PSQ_UNROLL
+      for (int a = 0; a < NY; ++a) s = fma(-M2[NY + i][a], V[a][j], s);
+      acc.A(i, j) = s;
+    }
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) acc.U(i, j) = M2[NY + i][NY + j];
+  }
+  // Z <- tria([Z | V^T])
+  double W[N][NY];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) W[i][a] = V[a][i];
+  tria_append<N, NY>([&](int i, int j) -> double& { return acc.Z(i, j); }, W);
+}
+
+// ---------------------------------------------------------------------------------------
+// Sweep 2 -- one square-root Kalman step x <- filter(x, step k) that also (SMOOTH) emits the
+// smoothing element of step k from the *same* triangularisation:
+//   tria([[F L, Q], [L, 0]]) = [[Phi11, 0], [Phi21, D]]                _smoothing.py:76-81
+// where Phi11 is the predicted factor the update needs (sequential/_filtering.py:80-86).
+// Returns the log-likelihood increment (_filtering.py:149-154) computed from Psi11.
+// ---------------------------------------------------------------------------------------
+template <int N, int NY, bool SMOOTH>
+PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
+  double F[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+  double mp[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = ldg(p.bq + i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], x.m[k], s);
+    mp[i] = s;
+  }
+  constexpr int RR = SMOOTH ? 2 * N : N;
+  double M1[RR][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
+      M1[i][j] = u;
+      M1[i][N + j] = ldg(p.Q + i * N + j);
+    }
+  if (SMOOTH) {
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < 2 * N; ++j) M1[RR - N + i][j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  }
+  house_rows<RR, 2 * N, N>(M1);
+  if (SMOOTH) {
+    // D = tria(bottom-right block)
+    double B[N][N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) B[i][j] = M1[RR - N + i][N + j];
+    house_rows<N, N, N - 1>(B);
+    // E = Phi21 Phi11^{-1}  (row-wise back substitution, _smoothing.py:83)
+    double inv[N];
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) inv[j] = 1.0 / M1[j][j];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      PSQ_UNROLL
+      for (int j = N - 1; j >= 0; --j) {
+        double s = M1[RR - N + i][j];
+        PSQ_UNROLL
+        for (int k = j + 1; k < N; ++k) s = fma(-se->E(i, k), M1[k][j], s);
+        se->E(i, j) = s * inv[j];
+      }
+      double gi = x.m[i];
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) gi = fma(-se->E(i, k), mp[k], gi);
+      se->g(i) = gi;                                                    // g = m - E (F m + b)
+      PSQ_UNROLL
+      for (int j = 0; j <= i; ++j) se->D(i, j) = B[i][j];
+    }
+  }
+  double M2[NY + N][N + NY];
+  build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
+  double inv2[NY], rr[NY];
+  psi11_inv_diag<N, NY>(M2, inv2);
+  double quad = 0.0, logdet = 0.0;
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double r = ldg(p.y + a) - ldg(p.c + a);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) r = fma(-ldg(p.H + a * N + k), mp[k], r);
+    PSQ_UNROLL
+    for (int q = 0; q < a; ++q) r = fma(-M2[a][q], rr[q], r);
+    rr[a] = r * inv2[a];
+    quad = fma(rr[a], rr[a], quad);
+    logdet += log(fabs(M2[a][a]));
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double mi = mp[i];
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) mi = fma(M2[NY + i][a], rr[a], mi);
+    x.m[i] = mi;
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) x.Lc(i, j) = M2[NY + i][NY + j];
+  }
+  return -0.5 * quad - logdet - NY * kHalfLog2Pi;
+}
+
+// Smoothing element of step k from the filtered state alone (used by sweep 3, which
+// recomputes instead of re-reading 8(2N^2+N) bytes per step).            _smoothing.py:72-85
+template <int N>
+PSQ_HD void smoothing_element(const Gauss<N>& x, const double* Fp, const double* Qp, const double* bqp,
+                              SElem<N>& se) {
+  double F[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = ldg(Fp + i * N + j);
+  double mp[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = ldg(bqp + i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], x.m[k], s);
+    mp[i] = s;
+  }
+  double M1[2 * N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
+      M1[i][j] = u;
+      M1[i][N + j] = ldg(Qp + i * N + j);
+    }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < 2 * N; ++j) M1[N + i][j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  house_rows<2 * N, 2 * N, N>(M1);
+  double B[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) B[i][j] = M1[N + i][N + j];
+  house_rows<N, N, N - 1>(B);
+  double inv[N];
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j) inv[j] = 1.0 / M1[j][j];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    PSQ_UNROLL
+    for (int j = N - 1; j >= 0; --j) {
+      double s = M1[N + i][j];
+      PSQ_UNROLL
+      for (int k = j + 1; k < N; ++k) s = fma(-se.E(i, k), M1[k][j], s);
+      se.E(i, j) = s * inv[j];
+    }
+    double gi = x.m[i];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) gi = fma(-se.E(i, k), mp[k], gi);
+    se.g(i) = gi;
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) se.D(i, j) = B[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Smoothing combine (_operators.py:118-125): e1 = accumulated LATER side, e2 = earlier side.
+//   g = E2 g1 + g2 ; E = E2 E1 ; D = tria([E2 D1 | D2])
+// ---------------------------------------------------------------------------------------
+template <int N>
+PSQ_HD SElem<N> smoothing_combine(const SElem<N>& e1, const SElem<N>& e2) {
+  SElem<N> o;
+  double M[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double gi = e2.g(i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) gi = fma(e2.E(i, k), e1.g(k), gi);
+    o.g(i) = gi;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0, d = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(e2.E(i, k), e1.E(k, j), s);
+      o.E(i, j) = s;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) d = fma(e2.E(i, k), e1.D(k, j), d);
+      M[i][j] = d;
+      M[i][N + j] = (j <= i) ? e2.D(i, j) : 0.0;
+    }
+  }
+  house_rows<N, 2 * N, N, N>(M);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) o.D(i, j) = M[i][j];
+  return o;
+}
+
+// Smoothing "apply": the same combine when only (g1, D1) of the later side is known -- i.e.
+// one RTS step x_s(k) from x_s(k+1):  m = E m_s + g ; L = tria([E L_s | D]).
+template <int N>
+PSQ_HD void smoothing_apply(Gauss<N>& xs, const SElem<N>& e2) {
+  double M[N][2 * N], mn[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double gi = e2.g(i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) gi = fma(e2.E(i, k), xs.m[k], gi);
+    mn[i] = gi;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double d = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) d = fma(e2.E(i, k), xs.Lc(k, j), d);
+      M[i][j] = d;
+      M[i][N + j] = (j <= i) ? e2.D(i, j) : 0.0;
+    }
+  }
+  house_rows<N, 2 * N, N, N>(M);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    xs.m[i] = mn[i];
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) xs.Lc(i, j) = M[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic filtering combine e1 (x) e2 (_operators.py:58-77), e1 = accumulated EARLIER side.
+// FULL = false evaluates only (b, U) of the result, which need only (b1, U1) of e1
+// ("apply": this is how a carry-in state is pushed through a chunk summary).
+// ---------------------------------------------------------------------------------------
+template <int N, bool FULL>
+PSQ_HD void filtering_combine_core(const FElem<N>* e1full, const double (&b1)[N], const double (&U1)[N][N],
+                                   const FElem<N>& e2, FElem<N>* out, double (&bo)[N], double (&Uo)[N][N]) {
+  // Xi = [[U1^T Z2, I], [Z2, 0]]                                         _operators.py:63-64
+  double Xi[2 * N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = (i > j ? i : j); k < N; ++k) s = fma(U1[k][i], e2.Z(k, j), s);
+      Xi[i][j] = s;
+      Xi[i][N + j] = (i == j) ? 1.0 : 0.0;
+      Xi[N + i][j] = (j <= i) ? e2.Z(i, j) : 0.0;
+      Xi[N + i][N + j] = 0.0;
+    }
+  house_rows<2 * N, 2 * N, N>(Xi);  // Xi11 = Xi[<N][<N] lower, Xi21 = Xi[N+.][<N], rest = pre-Xi22
+  // T1 = Xi11^{-1} U1^T   (N x N; U1^T is upper triangular so T1[i][j] needs k <= ... dense in general)
+  double inv[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) inv[i] = 1.0 / Xi[i][i];
+  double T1[N][N];
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j)
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = (j >= i) ? U1[j][i] : 0.0;  // (U1^T)[i][j]
+      PSQ_UNROLL
+      for (int k = 0; k < i; ++k) s = fma(-Xi[i][k], T1[k][j], s);
+      T1[i][j] = s * inv[i];
+    }
+  // W = A2 T1^T                                                      (S1 of the oracle)
+  double W[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(e2.A(i, k), T1[j][k], s);
+      W[i][j] = s;
+      W[i][N + j] = (j <= i) ? e2.U(i, j) : 0.0;
+    }
+  // b = A2 (t - T1^T Xi21^T t) + b2,  t = b1 + U1 U1^T eta2                  _operators.py:71
+  double t[N], u[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+    PSQ_UNROLL
+    for (int k = i; k < N; ++k) s = fma(U1[k][i], e2.eta(k), s);
+    u[i] = s;  // U1^T eta2
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = b1[i];
+    PSQ_UNROLL
+    for (int k = 0; k <= i; ++k) s = fma(U1[i][k], u[k], s);
+    t[i] = s;
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(Xi[N + k][i], t[k], s);
+    u[i] = s;  // Xi21^T t
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = t[i];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(-T1[k][i], u[k], s);
+    t[i] = s;
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = e2.b(i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(e2.A(i, k), t[k], s);
+    bo[i] = s;
+  }
+  if (FULL) {
+    const FElem<N>& e1 = *e1full;
+    // A = A2 A1 - W Xi21^T A1 = (A2 - W Xi21^T) A1                            _operators.py:70
+    double G[N][N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) {
+        double s = e2.A(i, j);
+        PSQ_UNROLL
+        for (int k = 0; k < N; ++k) s = fma(-W[i][k], Xi[N + j][k], s);
+        G[i][j] = s;
+      }
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        PSQ_UNROLL
+        for (int k = 0; k < N; ++k) s = fma(G[i][k], e1.A(k, j), s);
+        out->A(i, j) = s;
+      }
+    // eta = A1^T (s - Xi21 T1 s) + eta1,  s = eta2 - Z2 Z2^T b1             _operators.py:73-74
+    double sv[N], w[N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = i; k < N; ++k) s = fma(e2.Z(k, i), b1[k], s);
+      w[i] = s;  // Z2^T b1
+    }
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = e2.eta(i);
+      PSQ_UNROLL
+      for (int k = 0; k <= i; ++k) s = fma(-e2.Z(i, k), w[k], s);
+      sv[i] = s;
+    }
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(T1[i][k], sv[k], s);
+      w[i] = s;  // T1 s
+    }
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = sv[i];
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(-Xi[N + i][k], w[k], s);
+      sv[i] = s;
+    }
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = e1.eta(i);
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(e1.A(k, i), sv[k], s);
+      out->eta(i) = s;
+    }
+    // Z = tria([A1^T Xi22 | Z1]) with Xi22 = tria(bottom-right block)       _operators.py:75
+    double B[N][N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) B[i][j] = Xi[N + i][N + j];
+    house_rows<N, N, N - 1>(B);
+    double Zm[N][2 * N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        PSQ_UNROLL
+        for (int k = j; k < N; ++k) s = fma(e1.A(k, i), B[k][j], s);
+        Zm[i][j] = s;
+        Zm[i][N + j] = (j <= i) ? e1.Z(i, j) : 0.0;
+      }
+    house_rows<N, 2 * N, N, N>(Zm);
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j <= i; ++j) out->Z(i, j) = Zm[i][j];
+  }
+  // U = tria([W | U2])                                                        _operators.py:72
+  house_rows<N, 2 * N, N, N>(W);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) Uo[i][j] = (j <= i) ? W[i][j] : 0.0;
+}
+
+template <int N>
+PSQ_HD FElem<N> filtering_combine(const FElem<N>& e1, const FElem<N>& e2) {
+  FElem<N> o;
+  double b1[N], U1[N][N], bo[N], Uo[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    b1[i] = e1.b(i);
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) U1[i][j] = (j <= i) ? e1.U(i, j) : 0.0;
+  }
+  filtering_combine_core<N, true>(&e1, b1, U1, e2, &o, bo, Uo);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    o.b(i) = bo[i];
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) o.U(i, j) = Uo[i][j];
+  }
+  return o;
+}
+
+// x <- x (x) e2 keeping only the state part (mean, factor).
+template <int N>
+PSQ_HD void filtering_apply(Gauss<N>& x, const FElem<N>& e2) {
+  double b1[N], U1[N][N], bo[N], Uo[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    b1[i] = x.m[i];
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) U1[i][j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  }
+  filtering_combine_core<N, false>(nullptr, b1, U1, e2, nullptr, bo, Uo);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    x.m[i] = bo[i];
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) x.Lc(i, j) = Uo[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Reference-layout filtering element (with the prior folded into step 0), for the
+// element-level entry point psqrt_filter_elements.                     _filtering.py:115-146
+// m0/L0 may be null (zero prior).  L0 is a dense N x N factor (not nec. triangular).
+// ---------------------------------------------------------------------------------------
+template <int N, int NY>
+PSQ_HD void filtering_element(const StepPtrs& p, const double* m0, const double* L0,
+                              double* A, double* bo, double* U, double* eta, double* Z) {
+  double F[N][N], mz[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    mz[i] = m0 ? m0[i] : 0.0;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+  }
+  double m1[N], M1[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = ldg(p.bq + i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], mz[k], s);
+    m1[i] = s;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      if (L0) {
+        PSQ_UNROLL
+        for (int k = 0; k < N; ++k) u = fma(F[i][k], L0[k * N + j], u);
+      }
+      M1[i][j] = u;
+      M1[i][N + j] = ldg(p.Q + i * N + j);
+    }
+  }
+  house_rows<N, 2 * N, N>(M1);
+  double M2[NY + N][N + NY];
+  build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
+  double inv[NY];
+  psi11_inv_diag<N, NY>(M2, inv);
+  // HF = H F ; V = Psi11^{-1} HF ; r1 = Psi11^{-1}(y - H m1 - c) ; r2 = Psi11^{-1}(y - H bq - c)
+  double V[NY][N], r1[NY], r2[NY];
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double h[N];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
+    double ra = ldg(p.y + a) - ldg(p.c + a), rb = ra;
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) {
+      ra = fma(-h[k], m1[k], ra);
+      rb = fma(-h[k], ldg(p.bq + k), rb);
+    }
+    PSQ_UNROLL
+    for (int q = 0; q < a; ++q) {
+      ra = fma(-M2[a][q], r1[q], ra);
+      rb = fma(-M2[a][q], r2[q], rb);
+    }
+    r1[a] = ra * inv[a];
+    r2[a] = rb * inv[a];
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) s = fma(h[k], F[k][j], s);
+      PSQ_UNROLL
+      for (int q = 0; q < a; ++q) s = fma(-M2[a][q], V[q][j], s);
+      V[a][j] = s * inv[a];
+    }
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double bi = m1[i], e = 0.0;
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) {
+      bi = fma(M2[NY + i][a], r1[a], bi);
+      e = fma(V[a][i], r2[a], e);
+    }
+    bo[i] = bi;
+    eta[i] = e;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = F[i][j];
+      PSQ_UNROLL
+      for (int a = 0; a < NY; ++a) s = fma(-M2[NY + i][a], V[a][j], s);
+      A[i * N + j] = s;
+      U[i * N + j] = (j <= i) ? M2[NY + i][NY + j] : 0.0;
+    }
+  }
+  // Z = [V^T | 0] if N > NY else tria(V^T)                                _filtering.py:141-144
+  if (N > NY) {
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) Z[i * N + j] = (j < NY) ? V[j][i] : 0.0;
+  } else {
+    double Zt[N][NY];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int a = 0; a < NY; ++a) Zt[i][a] = V[a][i];
+    house_rows<N, NY, N>(Zt);
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) Z[i * N + j] = (j <= i) ? Zt[i][j] : 0.0;
+  }
+}
+
+// Log-likelihood term from the filtered state at k-1 (dense factor allowed)  _filtering.py:149-154
+template <int N, int NY>
+PSQ_HD double loglik_term(const StepPtrs& p, const double* m, const double* L) {
+  double F[N][N], mp[N], M1[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = ldg(p.bq + i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], m[k], s);
+    mp[i] = s;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) u = fma(F[i][k], L[k * N + j], u);
+      M1[i][j] = u;
+      M1[i][N + j] = ldg(p.Q + i * N + j);
+    }
+  }
+  house_rows<N, 2 * N, N>(M1);
+  double S[NY][N + NY];
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) s = fma(ldg(p.H + a * N + k), M1[k][j], s);
+      S[a][j] = s;
+    }
+    PSQ_UNROLL
+    for (int q = 0; q < NY; ++q) S[a][N + q] = ldg(p.R + a * NY + q);
+  }
+  house_rows<NY, N + NY, NY>(S);
+  double rr[NY], quad = 0.0, logdet = 0.0;
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double r = ldg(p.y + a) - ldg(p.c + a);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) r = fma(-ldg(p.H + a * N + k), mp[k], r);
+    PSQ_UNROLL
+    for (int q = 0; q < a; ++q) r = fma(-S[a][q], rr[q], r);
+    rr[a] = r / S[a][a];
+    quad = fma(rr[a], rr[a], quad);
+    logdet += log(fabs(S[a][a]));
+  }
+  return -0.5 * quad - logdet - NY * kHalfLog2Pi;
+}
+
+// Rank-one Cholesky update, literal column sweep of _utils.py:39-81 (incl. the
+// non-finite -> 0 guard, line 80).  L is dense row-major N x N (lower part used).
+template <int N>
+PSQ_HD void chol_update(double (&L)[N][N], double (&w)[N], double mult) {
+  double b = 1.0;
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j) {
+    const double d = L[j][j];
+    const double wj = w[j];
+    const double nd = sqrt(fma(d, d, mult / b * (wj * wj)));
+    const double gamma = fma(d * d, b, mult * (wj * wj));
+    const double wd = wj / d;
+    const double cg = mult * wj / gamma;
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      const double col = L[i][j];  // entries above the diagonal are 0 and stay irrelevant
+      w[i] = fma(-wd, col, w[i]);
+      double nc = nd * (col / d + cg * w[i]);
+      if (i == j) nc = nd;
+      if (i < j) nc = 0.0;
+      L[i][j] = isfinite(nc) ? nc : 0.0;
+    }
+    b = fma(mult, wd * wd, b);
+  }
+}
+
+}  // namespace psq

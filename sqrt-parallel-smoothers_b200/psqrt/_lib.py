@@ -1,0 +1,463 @@
+"""ctypes binding of libpsqrt.so (C ABI in include/psqrt.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: device memory, the current stream, and torch.distributed.  Every
+numerical kernel runs inside libpsqrt.so.  There is NO fallback: if the library is missing or
+a tensor is not an fp64 CUDA tensor the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpsqrt.so")
+_lib = None
+
+c_double_p = ctypes.c_void_p  # raw device addresses
+
+
+class PsqrtError(RuntimeError):
+    pass
+
+
+class _Ssm(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("F", "cholQ", "b", "H", "cholR", "c")] + \
+               [(n, ctypes.c_int64) for n in ("F_ts", "cholQ_ts", "b_ts", "H_ts", "cholR_ts", "c_ts")] + \
+               [(n, ctypes.c_int64) for n in ("F_bs", "cholQ_bs", "b_bs", "H_bs", "cholR_bs", "c_bs")]
+
+
+class Plan(ctypes.Structure):
+    _fields_ = [("chunk_len", ctypes.c_int32), ("n_chunks", ctypes.c_int64), ("n_chunks_pad", ctypes.c_int64),
+                ("n_warps", ctypes.c_int64), ("nf_filter", ctypes.c_int32), ("nf_smoother", ctypes.c_int32)]
+
+
+EXPORTS = (
+    "psqrt_version", "psqrt_error_string", "psqrt_supported", "psqrt_get_plan", "psqrt_workspace_bytes",
+    "psqrt_filter_smoother", "psqrt_smoother", "psqrt_filter_reduce", "psqrt_carry_filter", "psqrt_filter_apply",
+    "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
+    "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
+    "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched",
+)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load libpsqrt.so (built in-tree by sqrt-parallel-smoothers_b200/build.py).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise PsqrtError(f"{_LIB_PATH} is missing: build it with `python sqrt-parallel-smoothers_b200/build.py` "
+                         f"(or __graft_entry__.build()).  There is no CPU / eager fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.psqrt_error_string.restype = ctypes.c_char_p
+    lib.psqrt_workspace_bytes.restype = ctypes.c_size_t
+    lib.psqrt_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int]
+    lib.psqrt_get_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                   ctypes.POINTER(Plan)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().psqrt_error_string(rc).decode()
+        raise PsqrtError(f"{what} failed: {msg} (code {rc})")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise PsqrtError(f"expected a contiguous fp64 CUDA tensor, got {t.dtype} on {t.device} "
+                         f"(contiguous={t.is_contiguous()})")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device: torch.device, slot: int = 0) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def supported(nx: int, ny: int = 0) -> bool:
+    return bool(load().psqrt_supported(int(nx), int(ny)))
+
+
+def get_plan(nx: int, ny: int, T: int, batch: int = 1, chunk_len: int = 0) -> Plan:
+    p = Plan()
+    _check(load().psqrt_get_plan(nx, ny, T, batch, chunk_len, ctypes.byref(p)), "psqrt_get_plan")
+    return p
+
+
+def _require(nx: int, ny: int):
+    if not supported(nx, ny):
+        raise PsqrtError(f"libpsqrt.so has no kernels for nx={nx}, ny={ny} "
+                         f"(compiled: nx in 1,2,3,4,5,6,8 and ny in 1..4)")
+
+
+class LinearizedSSM:
+    """Per-step linearised model (F, cholQ, b, H, cholR, c): each entry is a tensor whose leading
+    dims are [] (shared), [T] (per step) or [B, T] / [B] (per sequence)."""
+
+    def __init__(self, F, cholQ, b, H=None, cholR=None, c=None):
+        self.F, self.cholQ, self.b, self.H, self.cholR, self.c = F, cholQ, b, H, cholR, c
+
+    def struct(self, T: int, batch: int, keep: list) -> _Ssm:
+        s = _Ssm()
+        for name, core in (("F", 2), ("cholQ", 2), ("b", 1), ("H", 2), ("cholR", 2), ("c", 1)):
+            t = getattr(self, name)
+            if t is None:
+                setattr(s, name, None)
+                continue
+            t = t.contiguous()
+            keep.append(t)
+            lead = t.shape[:t.dim() - core]
+            size = 1
+            for d in t.shape[t.dim() - core:]:
+                size *= d
+            ts = bs = 0
+            if len(lead) == 0:
+                pass
+            elif len(lead) == 1:
+                if lead[0] != T:
+                    raise PsqrtError(f"{name}: leading dim {lead[0]} != T={T}")
+                ts = size
+            elif len(lead) == 2:
+                if lead[0] != batch or lead[1] not in (1, T):
+                    raise PsqrtError(f"{name}: leading dims {tuple(lead)} != (batch={batch}, T={T})")
+                ts = size if lead[1] == T else 0
+                bs = size * lead[1]
+            else:
+                raise PsqrtError(f"{name}: too many leading dims {tuple(lead)}")
+            setattr(s, name, _ptr(t).value)
+            setattr(s, name + "_ts", ts)
+            setattr(s, name + "_bs", bs)
+        return s
+
+
+def _batchify(x: torch.Tensor, core: int):
+    """-> ([B, ...] tensor, had_batch)"""
+    if x.dim() == core:
+        return x.unsqueeze(0), False
+    return x, True
+
+
+def filter_smoother(ssm: LinearizedSSM, y: torch.Tensor, m0: torch.Tensor, L0: torch.Tensor, *, smooth: bool = True,
+                    loglik: bool = False, chunk_len: int = 0):
+    """One pass.  y [T, ny] or [B, T, ny]; m0 [nx] / [B, nx]; L0 lower-triangular [nx, nx] / [B, nx, nx].
+    Returns (fm, fL, sm, sL, ell) with sm/sL/ell None when not requested."""
+    lib = load()
+    yb, had_b = _batchify(y, 2)
+    B, T, ny = yb.shape
+    m0b, _ = _batchify(m0, 1)
+    L0b, _ = _batchify(L0, 2)
+    nx = m0b.shape[-1]
+    _require(nx, ny)
+    if m0b.shape[0] != B:
+        m0b = m0b.expand(B, nx)
+        L0b = L0b.expand(B, nx, nx)
+    yb, m0b, L0b = yb.contiguous(), m0b.contiguous(), L0b.contiguous()
+    dev = yb.device
+    fm = torch.empty((B, T + 1, nx), dtype=torch.float64, device=dev)
+    fL = torch.empty((B, T + 1, nx, nx), dtype=torch.float64, device=dev)
+    sm = torch.empty_like(fm) if smooth else None
+    sL = torch.empty_like(fL) if smooth else None
+    ell = torch.empty((B,), dtype=torch.float64, device=dev) if loglik else None
+    nbytes = lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len)
+    ws = workspace(nbytes, dev)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_filter_smoother(ctypes.byref(s), _ptr(yb), _ptr(m0b), _ptr(L0b), nx, ny,
+                                       ctypes.c_int64(T), ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(sm),
+                                       _ptr(sL), _ptr(ell), ctypes.c_void_p(ws.data_ptr()),
+                                       ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_filter_smoother")
+    if not had_b:
+        fm, fL = fm[0], fL[0]
+        sm, sL = (sm[0], sL[0]) if smooth else (None, None)
+        ell = ell[0] if loglik else None
+    return fm, fL, sm, sL, ell
+
+
+def smoother(ssm: LinearizedSSM, fm: torch.Tensor, fL: torch.Tensor, *, chunk_len: int = 0):
+    lib = load()
+    fmb, had_b = _batchify(fm, 2)
+    fLb, _ = _batchify(fL, 3)
+    fmb, fLb = fmb.contiguous(), fLb.contiguous()
+    B, Tp1, nx = fmb.shape
+    T = Tp1 - 1
+    _require(nx, 0)
+    sm, sL = torch.empty_like(fmb), torch.empty_like(fLb)
+    if T == 0:
+        sm.copy_(fmb)
+        sL.copy_(fLb)
+    else:
+        nbytes = lib.psqrt_workspace_bytes(0, nx, 0, T, B, chunk_len)
+        ws = workspace(nbytes, fmb.device)
+        keep = []
+        s = ssm.struct(T, B, keep)
+        with torch.cuda.device(fmb.device):
+            rc = lib.psqrt_smoother(ctypes.byref(s), _ptr(fmb), _ptr(fLb), nx, ctypes.c_int64(T), ctypes.c_int64(B),
+                                    chunk_len, _ptr(sm), _ptr(sL), ctypes.c_void_p(ws.data_ptr()),
+                                    ctypes.c_size_t(ws.numel()), _stream())
+        _check(rc, "psqrt_smoother")
+    return (sm, sL) if had_b else (sm[0], sL[0])
+
+
+# ---- staged calls (time-sharded runs; see psqrt/dist.py) ---------------------------------------
+def filter_reduce(ssm, y, nx, chunk_len=0):
+    lib = load()
+    B, T, ny = y.shape
+    _require(nx, ny)
+    plan = get_plan(nx, ny, T, B, chunk_len)
+    total = torch.empty((B, plan.nf_filter), dtype=torch.float64, device=y.device)
+    ws = workspace(lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len), y.device)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    with torch.cuda.device(y.device):
+        rc = lib.psqrt_filter_reduce(ctypes.byref(s), _ptr(y), nx, ny, ctypes.c_int64(T), ctypes.c_int64(B), chunk_len,
+                                     _ptr(total), ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()),
+                                     _stream())
+    _check(rc, "psqrt_filter_reduce")
+    return total
+
+
+def carry_filter(totals, rank, m0, L0):
+    lib = load()
+    B, nx = m0.shape
+    cm, cL = torch.empty_like(m0), torch.empty_like(L0)
+    with torch.cuda.device(m0.device):
+        rc = lib.psqrt_carry_filter(_ptr(totals), rank, ctypes.c_int64(B), nx, _ptr(m0), _ptr(L0), _ptr(cm), _ptr(cL),
+                                    _stream())
+    _check(rc, "psqrt_carry_filter")
+    return cm, cL
+
+
+def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_len=0):
+    lib = load()
+    B, T, ny = y.shape
+    nx = carry_m.shape[-1]
+    plan = get_plan(nx, ny, T, B, chunk_len)
+    dev = y.device
+    fm = torch.empty((B, T + 1, nx), dtype=torch.float64, device=dev)
+    fL = torch.empty((B, T + 1, nx, nx), dtype=torch.float64, device=dev)
+    ell = torch.empty((B,), dtype=torch.float64, device=dev) if loglik else None
+    stotal = torch.empty((B, plan.nf_smoother), dtype=torch.float64, device=dev) if smooth else None
+    ws = workspace(lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len), dev)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_filter_apply(ctypes.byref(s), _ptr(y), _ptr(carry_m), _ptr(carry_L), nx, ny, ctypes.c_int64(T),
+                                    ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(ell), _ptr(stotal),
+                                    ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_filter_apply")
+    return fm, fL, ell, stotal
+
+
+def carry_smoother(totals, rank, n_ranks, mT, LT):
+    lib = load()
+    B, nx = mT.shape
+    cm, cL = torch.empty_like(mT), torch.empty_like(LT)
+    with torch.cuda.device(mT.device):
+        rc = lib.psqrt_carry_smoother(_ptr(totals), rank, n_ranks, ctypes.c_int64(B), nx, _ptr(mT), _ptr(LT), _ptr(cm),
+                                      _ptr(cL), _stream())
+    _check(rc, "psqrt_carry_smoother")
+    return cm, cL
+
+
+def smoother_apply(ssm, fm, fL, carry_m, carry_L, *, write_terminal=True, chunk_len=0):
+    lib = load()
+    B, Tp1, nx = fm.shape
+    T = Tp1 - 1
+    sm, sL = torch.empty_like(fm), torch.empty_like(fL)
+    ws = workspace(lib.psqrt_workspace_bytes(0, nx, 0, T, B, chunk_len), fm.device)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    with torch.cuda.device(fm.device):
+        rc = lib.psqrt_smoother_apply(ctypes.byref(s), _ptr(fm), _ptr(fL), _ptr(carry_m), _ptr(carry_L),
+                                      int(write_terminal), nx, ctypes.c_int64(T), ctypes.c_int64(B), chunk_len,
+                                      _ptr(sm), _ptr(sL), ctypes.c_void_p(ws.data_ptr()),
+                                      ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_smoother_apply")
+    return sm, sL
+
+
+# ---- element-level seams ------------------------------------------------------------------------
+def filter_elements(ssm, y, m0=None, L0=None):
+    lib = load()
+    yb, had_b = _batchify(y, 2)
+    yb = yb.contiguous()
+    B, T, ny = yb.shape
+    keep = []
+    s = ssm.struct(T, B, keep)
+    nx = ssm.F.shape[-1]
+    _require(nx, ny)
+    dev = yb.device
+    A = torch.empty((B, T, nx, nx), dtype=torch.float64, device=dev)
+    U, Z = torch.empty_like(A), torch.empty_like(A)
+    b = torch.empty((B, T, nx), dtype=torch.float64, device=dev)
+    eta = torch.empty_like(b)
+    if m0 is not None:
+        m0 = _batchify(m0, 1)[0].expand(B, nx).contiguous()
+        L0 = _batchify(L0, 2)[0].expand(B, nx, nx).contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_filter_elements(ctypes.byref(s), _ptr(yb), _ptr(m0), _ptr(L0), nx, ny, ctypes.c_int64(T),
+                                       ctypes.c_int64(B), _ptr(A), _ptr(b), _ptr(U), _ptr(eta), _ptr(Z), _stream())
+    _check(rc, "psqrt_filter_elements")
+    out = (A, b, U, eta, Z)
+    return out if had_b else tuple(o[0] for o in out)
+
+
+def filter_scan(A, b, U, eta, Z, *, chunk_len=0):
+    lib = load()
+    Ab, had_b = _batchify(A, 3)
+    args = [_batchify(t, c)[0].contiguous() for t, c in ((A, 3), (b, 2), (U, 3), (eta, 2), (Z, 3))]
+    B, T, nx, _ = Ab.shape
+    _require(nx, 0)
+    means = torch.empty((B, T, nx), dtype=torch.float64, device=Ab.device)
+    chols = torch.empty((B, T, nx, nx), dtype=torch.float64, device=Ab.device)
+    ws = workspace(lib.psqrt_workspace_bytes(1, nx, 0, T, B, chunk_len), Ab.device)
+    with torch.cuda.device(Ab.device):
+        rc = lib.psqrt_filter_scan(*[_ptr(t) for t in args], nx, ctypes.c_int64(T), ctypes.c_int64(B), chunk_len,
+                                   _ptr(means), _ptr(chols), ctypes.c_void_p(ws.data_ptr()),
+                                   ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_filter_scan")
+    return (means, chols) if had_b else (means[0], chols[0])
+
+
+def smoother_elements(ssm, fm, fL):
+    lib = load()
+    fmb, had_b = _batchify(fm, 2)
+    fLb = _batchify(fL, 3)[0].contiguous()
+    fmb = fmb.contiguous()
+    B, Tp1, nx = fmb.shape
+    T = Tp1 - 1
+    _require(nx, 0)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    g = torch.empty_like(fmb)
+    E, D = torch.empty_like(fLb), torch.empty_like(fLb)
+    with torch.cuda.device(fmb.device):
+        rc = lib.psqrt_smoother_elements(ctypes.byref(s), _ptr(fmb), _ptr(fLb), nx, ctypes.c_int64(T),
+                                         ctypes.c_int64(B), _ptr(g), _ptr(E), _ptr(D), _stream())
+    _check(rc, "psqrt_smoother_elements")
+    out = (g, E, D)
+    return out if had_b else tuple(o[0] for o in out)
+
+
+def smoother_scan(g, E, D, *, chunk_len=0):
+    lib = load()
+    gb, had_b = _batchify(g, 2)
+    args = [_batchify(t, c)[0].contiguous() for t, c in ((g, 2), (E, 3), (D, 3))]
+    B, n, nx = gb.shape
+    _require(nx, 0)
+    means = torch.empty((B, n, nx), dtype=torch.float64, device=gb.device)
+    chols = torch.empty((B, n, nx, nx), dtype=torch.float64, device=gb.device)
+    ws = workspace(lib.psqrt_workspace_bytes(1, nx, 0, n, B, chunk_len), gb.device)
+    with torch.cuda.device(gb.device):
+        rc = lib.psqrt_smoother_scan(*[_ptr(t) for t in args], nx, ctypes.c_int64(n), ctypes.c_int64(B), chunk_len,
+                                     _ptr(means), _ptr(chols), ctypes.c_void_p(ws.data_ptr()),
+                                     ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_smoother_scan")
+    return (means, chols) if had_b else (means[0], chols[0])
+
+
+def loglik_terms(ssm, y, fm, fL):
+    lib = load()
+    yb, had_b = _batchify(y, 2)
+    yb = yb.contiguous()
+    fmb = _batchify(fm, 2)[0].contiguous()
+    fLb = _batchify(fL, 3)[0].contiguous()
+    B, T, ny = yb.shape
+    nx = fmb.shape[-1]
+    _require(nx, ny)
+    keep = []
+    s = ssm.struct(T, B, keep)
+    terms = torch.empty((B, T), dtype=torch.float64, device=yb.device)
+    with torch.cuda.device(yb.device):
+        rc = lib.psqrt_loglik_terms(ctypes.byref(s), _ptr(yb), _ptr(fmb), _ptr(fLb), nx, ny, ctypes.c_int64(T),
+                                    ctypes.c_int64(B), _ptr(terms), _stream())
+    _check(rc, "psqrt_loglik_terms")
+    return terms if had_b else terms[0]
+
+
+def filter_combine(e1: Sequence[torch.Tensor], e2: Sequence[torch.Tensor]):
+    """sqrt_filtering_operator on n pairs (leading axis), or on a single pair."""
+    lib = load()
+    single = e1[0].dim() == 2
+    cores = (3, 2, 3, 2, 3)
+    a1 = [(t.unsqueeze(0) if single else t).contiguous() for t in e1]
+    a2 = [(t.unsqueeze(0) if single else t).contiguous() for t in e2]
+    n, nx = a1[1].shape
+    _require(nx, 0)
+    outs = [torch.empty_like(t) for t in a1]
+    with torch.cuda.device(a1[0].device):
+        rc = lib.psqrt_filter_combine(*[_ptr(t) for t in a1], *[_ptr(t) for t in a2], nx, ctypes.c_int64(n),
+                                      *[_ptr(t) for t in outs], _stream())
+    _check(rc, "psqrt_filter_combine")
+    del cores
+    return tuple(o[0] for o in outs) if single else tuple(outs)
+
+
+def smoother_combine(e1, e2):
+    lib = load()
+    single = e1[0].dim() == 1
+    a1 = [(t.unsqueeze(0) if single else t).contiguous() for t in e1]
+    a2 = [(t.unsqueeze(0) if single else t).contiguous() for t in e2]
+    n, nx = a1[0].shape
+    _require(nx, 0)
+    outs = [torch.empty_like(t) for t in a1]
+    with torch.cuda.device(a1[0].device):
+        rc = lib.psqrt_smoother_combine(*[_ptr(t) for t in a1], *[_ptr(t) for t in a2], nx, ctypes.c_int64(n),
+                                        *[_ptr(t) for t in outs], _stream())
+    _check(rc, "psqrt_smoother_combine")
+    return tuple(o[0] for o in outs) if single else tuple(outs)
+
+
+def tria(A: torch.Tensor) -> torch.Tensor:
+    """tria(A) of parsmooth/_utils.py:22-24 for [..., rows, cols] (rows in the compiled set)."""
+    lib = load()
+    rows, cols = A.shape[-2:]
+    lead = A.shape[:-2]
+    Ab = A.reshape(-1, rows, cols).contiguous()
+    L = torch.empty((Ab.shape[0], rows, rows), dtype=torch.float64, device=A.device)
+    if Ab.shape[0] > 0:
+        with torch.cuda.device(A.device):
+            rc = lib.psqrt_tria_batched(_ptr(Ab), _ptr(L), rows, cols, ctypes.c_int64(Ab.shape[0]), _stream())
+        _check(rc, "psqrt_tria_batched")
+    return L.reshape(*lead, rows, rows)
+
+
+def chol_update_many(L: torch.Tensor, V: torch.Tensor, alpha: float) -> torch.Tensor:
+    """cholesky_update_many of parsmooth/_utils.py:13-19: L [..., n, n], V [..., k, n]."""
+    lib = load()
+    n = L.shape[-1]
+    k = V.shape[-2]
+    lead = L.shape[:-2]
+    Lb = L.reshape(-1, n, n).contiguous().clone()
+    Vb = V.reshape(-1, k, n).contiguous()
+    if Lb.shape[0] > 0:
+        with torch.cuda.device(L.device):
+            rc = lib.psqrt_chol_update_batched(_ptr(Lb), _ptr(Vb), n, k, ctypes.c_double(alpha),
+                                               ctypes.c_int64(Lb.shape[0]), _stream())
+        _check(rc, "psqrt_chol_update_batched")
+    return Lb.reshape(*lead, n, n)

@@ -1,0 +1,179 @@
+"""User-facing API: a drop-in for parsmooth.methods on the parallel square-root path
+(reference: parsmooth/methods.py:14-76 -> parallel/_filtering.py:13-61, parallel/_smoothing.py:14-57).
+
+Same names, positional order and return conventions as the reference.  What differs:
+* arrays are fp64 torch CUDA tensors (NumPy / CPU inputs are moved to the current CUDA device);
+* ``parallel=False`` and ``MVNStandard`` inputs raise NotImplementedError -- this package is the
+  sqrt=True, parallel=True path only and has no CPU or covariance-form fallback;
+* the scan is the chunked three-sweep scheme of libpsqrt.so instead of jax.lax.associative_scan.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from ._base import MVNSqrt, MVNStandard, FunctionalModel, ConditionalMomentsModel, are_inputs_compatible
+from ._lib import LinearizedSSM
+
+__all__ = ["filtering", "smoothing", "filter_smoother", "iterated_smoothing"]
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.PsqrtError("psqrt needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _t(x, dev):
+    return torch.as_tensor(x, dtype=torch.float64).to(dev)
+
+
+def _mvn(x, dev):
+    if isinstance(x, MVNStandard):
+        raise NotImplementedError("psqrt implements the square-root path only (MVNSqrt); "
+                                  "covariance-form inputs are out of scope")
+    if not isinstance(x, MVNSqrt):
+        raise TypeError(f"expected MVNSqrt, got {type(x)}")
+    return MVNSqrt(_t(x.mean, dev), _t(x.chol, dev))
+
+
+def _model(model, dev):
+    if isinstance(model, FunctionalModel):
+        return FunctionalModel(model.function, _mvn(model.mvn, dev))
+    if isinstance(model, ConditionalMomentsModel):
+        return model
+    raise TypeError(f"expected FunctionalModel or ConditionalMomentsModel, got {type(model)}")
+
+
+def _check_parallel(parallel):
+    if not parallel:
+        raise NotImplementedError("psqrt is the parallel=True path; the sequential algorithms are not part of it")
+
+
+def _default_nominal(T1, nx, dev):
+    """zeros mean, identity chol, length T+1 (parallel/_filtering.py:25-28, _smoothing.py:22-28);
+    the identity is a stride-0 view, nothing of size T is allocated for it."""
+    mean = torch.zeros((T1, nx), dtype=torch.float64, device=dev)
+    chol = torch.eye(nx, dtype=torch.float64, device=dev).expand(T1, nx, nx)
+    return MVNSqrt(mean, chol)
+
+
+def _slice(nominal, sl):
+    return MVNSqrt(nominal.mean[sl], nominal.chol[sl])
+
+
+def _linearize(lin, transition_model, observation_model, nominal):
+    """transition at nominal[:-1], observation at nominal[1:] (parallel/_filtering.py:103-104,117-119)."""
+    F, cholQ, b = lin(transition_model, _slice(nominal, slice(None, -1)))
+    if observation_model is None:
+        return LinearizedSSM(F, cholQ, b)
+    H, cholR, c = lin(observation_model, _slice(nominal, slice(1, None)))
+    return LinearizedSSM(F, cholQ, b, H, cholR, c)
+
+
+def _prior_factor(L0):
+    """The kernels read the lower triangle of the carry-in factor; any other square root of the
+    prior covariance is first triangularised (tria, parsmooth/_utils.py:22-24)."""
+    return _lib.tria(L0)
+
+
+def _run(observations, x0, transition_model, observation_model, lin, nominal, smooth, loglik):
+    dev = _device()
+    ys = _t(observations, dev)
+    x0 = _mvn(x0, dev)
+    transition_model = _model(transition_model, dev)
+    observation_model = _model(observation_model, dev)
+    T = ys.shape[0]
+    nx = x0.mean.shape[-1]
+    if nominal is not None:
+        are_inputs_compatible(x0, nominal)
+        nominal = _mvn(nominal, dev)
+    else:
+        nominal = _default_nominal(T + 1, nx, dev)
+    ssm = _linearize(lin, transition_model, observation_model, nominal)
+    fm, fL, sm, sL, ell = _lib.filter_smoother(ssm, ys, x0.mean, _prior_factor(x0.chol), smooth=smooth,
+                                               loglik=loglik)
+    # index 0 of the filtered trajectory is x0 itself (parallel/_filtering.py:45-46)
+    fm[0].copy_(x0.mean)
+    fL[0].copy_(x0.chol)
+    return MVNSqrt(fm, fL), (MVNSqrt(sm, sL) if smooth else None), ell
+
+
+def filtering(observations, x0, transition_model, observation_model, linearization_method: Callable,
+              nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True,
+              return_loglikelihood: bool = False):
+    """parsmooth.methods.filtering (methods.py:14-26) for MVNSqrt x0, parallel=True."""
+    _check_parallel(parallel)
+    filt, _, ell = _run(observations, x0, transition_model, observation_model, linearization_method,
+                        nominal_trajectory, smooth=False, loglik=return_loglikelihood)
+    if return_loglikelihood:
+        return filt, ell
+    return filt
+
+
+def smoothing(transition_model, filter_trajectory, linearization_method: Callable,
+              nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True):
+    """parsmooth.methods.smoothing (methods.py:29-35; parallel/_smoothing.py:14-57)."""
+    _check_parallel(parallel)
+    dev = _device()
+    ft = _mvn(filter_trajectory, dev)
+    transition_model = _model(transition_model, dev)
+    T1, nx = ft.mean.shape
+    if nominal_trajectory is not None:
+        are_inputs_compatible(filter_trajectory, nominal_trajectory)
+        nominal = _mvn(nominal_trajectory, dev)
+    else:
+        nominal = _default_nominal(T1, nx, dev)
+    ssm = _linearize(linearization_method, transition_model, None, nominal)
+    fL = ft.chol
+    if bool((torch.triu(fL, 1) != 0).any()):      # kernels read lower triangles only
+        fL = _lib.tria(fL)
+    sm, sL = _lib.smoother(ssm, ft.mean, fL)
+    return MVNSqrt(sm, sL)
+
+
+def filter_smoother(observations, x0, transition_model, observation_model, linearization_method: Callable,
+                    nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True):
+    """parsmooth.methods.filter_smoother (methods.py:38-47), fused into one pass: the transition
+    model is linearised once and the smoothing elements come out of the filter's own
+    triangularisation."""
+    _check_parallel(parallel)
+    _, smoothed, _ = _run(observations, x0, transition_model, observation_model, linearization_method,
+                          nominal_trajectory, smooth=True, loglik=False)
+    return smoothed
+
+
+def _default_criterion(_i, nominal_traj_prev, curr_nominal_traj):
+    """methods.py:50-51"""
+    return torch.mean((nominal_traj_prev.mean - curr_nominal_traj.mean) ** 2) > 1e-6
+
+
+def fixed_point(f, x0, criterion):
+    """parsmooth/_utils.py:103-105,136-146: carry (1, x0, f(x0)); iterate while criterion(i, prev, x)."""
+    i, x_prev, x = 1, x0, f(x0)
+    while bool(criterion(i, x_prev, x)):
+        i, x_prev, x = i + 1, x, f(x)
+    return x
+
+
+def iterated_smoothing(observations, x0, transition_model, observation_model, linearization_method: Callable,
+                       init_nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True,
+                       criterion: Callable = _default_criterion, return_loglikelihood: bool = False):
+    """parsmooth.methods.iterated_smoothing (methods.py:54-76)."""
+    _check_parallel(parallel)
+    if init_nominal_trajectory is None:
+        init_nominal_trajectory = filter_smoother(observations, x0, transition_model, observation_model,
+                                                  linearization_method, None, parallel)
+
+    def fun_to_iter(curr_nominal_traj):
+        return filter_smoother(observations, x0, transition_model, observation_model, linearization_method,
+                               curr_nominal_traj, parallel)
+
+    nominal_traj = fixed_point(fun_to_iter, init_nominal_trajectory, criterion)
+    if return_loglikelihood:
+        _, ell = filtering(observations, x0, transition_model, observation_model, linearization_method,
+                           nominal_traj, parallel, return_loglikelihood=True)
+        return nominal_traj, ell
+    return nominal_traj

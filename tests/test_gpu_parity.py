@@ -1,0 +1,427 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libpsqrt.so, via psqrt._lib / psqrt.methods)
+against the NumPy oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: means 1e-9 relative, covariances compared as L L^T 1e-9 relative
+(QR sign ambiguity, parsmooth/_utils.py:22-24), log-likelihood 1e-8 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import parsmooth_np as O
+from _cases import LLt, lgssm_case, oracle_from_ssm, oracle_lgssm_models, rel_err, time_varying_case
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+TOL_ELL = 1e-8
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _g(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=_dev())
+
+
+def _ssm(case):
+    from psqrt._lib import LinearizedSSM
+    return LinearizedSSM(*[_g(case[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")])
+
+
+def _check_traj(name, m, L, om, oL, tol=TOL):
+    em, eL = rel_err(m.cpu().numpy(), om), rel_err(LLt(L.cpu().numpy()), LLt(oL))
+    assert em < tol and eL < tol, f"{name}: mean err {em:.3e}, LL^T err {eL:.3e}"
+    return em, eL
+
+
+def test_library_loaded_from_tree():
+    from psqrt import _lib
+    lib = _lib.load()
+    assert lib.psqrt_version() == 100
+    assert "sqrt-parallel-smoothers_b200" in _lib.lib_path()
+
+
+@pytest.mark.parametrize("n,ny,T,K", [(4, 2, 1000, 0), (4, 2, 1000, 7), (4, 2, 1000, 1), (5, 2, 333, 4), (1, 1, 100, 3),
+                                      (1, 3, 50, 2), (2, 3, 77, 5), (3, 3, 500, 16), (4, 2, 5, 2), (2, 1, 1, 1),
+                                      (6, 4, 257, 3), (8, 4, 130, 0), (3, 1, 31, 1), (3, 1, 32, 1), (3, 1, 33, 1),
+                                      (4, 2, 4097, 1), (4, 2, 12289, 3)])
+def test_pass_vs_oracle_lgssm(n, ny, T, K):
+    """Whole filter + smoother pass + ell on a time-invariant LGSSM, every chunk length regime
+    (ragged tails, single chunk, > 1 CTA, > 32 warps in the mid scan)."""
+    from psqrt import _lib
+    case = lgssm_case(n, ny, T, seed=100 * n + ny)
+    fm, fL, sm, sL, ell = _lib.filter_smoother(_ssm(case), _g(case["ys"]), _g(case["m0"]), _g(case["L0"]),
+                                               smooth=True, loglik=True, chunk_len=K)
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    _check_traj("filtered", fm, fL, ofm, ofc)
+    _check_traj("smoothed", sm, sL, osm, osc)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+
+
+@pytest.mark.parametrize("n,ny,T,K", [(4, 2, 300, 0), (5, 2, 1000, 5), (2, 2, 64, 1), (3, 4, 200, 3)])
+def test_pass_vs_oracle_time_varying(n, ny, T, K):
+    """Per-step (F, cholQ, b, H, cholR, c): what a nonlinear model's linearisation feeds the scan."""
+    from psqrt import _lib
+    case = time_varying_case(n, ny, T, seed=7 * n + ny)
+    fm, fL, sm, sL, ell = _lib.filter_smoother(_ssm(case), _g(case["ys"]), _g(case["m0"]), _g(case["L0"]),
+                                               smooth=True, loglik=True, chunk_len=K)
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    _check_traj("filtered", fm, fL, ofm, ofc)
+    _check_traj("smoothed", sm, sL, osm, osc)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+
+
+def test_pass_vs_sequential_oracle():
+    """Second oracle: the reference's sequential sqrt filter / smoother (sequential/_filtering.py, _smoothing.py)."""
+    from psqrt import _lib
+    case = lgssm_case(4, 2, 400, seed=3)
+    tm, om = oracle_lgssm_models(case)
+    nominal = O._default_nominal(case["m0"], 401)
+    fs, ells = O.seq_filtering(case["ys"], O.MVNSqrt(case["m0"], case["L0"]), tm, om, O.extended, nominal, True)
+    ss = O.seq_smoothing(tm, fs, O.extended, nominal)
+    fm, fL, sm, sL, ell = _lib.filter_smoother(_ssm(case), _g(case["ys"]), _g(case["m0"]), _g(case["L0"]),
+                                               smooth=True, loglik=True)
+    _check_traj("filtered", fm, fL, fs.mean, fs.chol)
+    _check_traj("smoothed", sm, sL, ss.mean, ss.chol)
+    assert abs(ell.item() - ells) <= TOL_ELL * abs(ells)
+
+
+def test_batched_pass():
+    """batch axis: independent sequences sharing the model (config 5 shape)."""
+    from psqrt import _lib
+    from psqrt._lib import LinearizedSSM
+    n, ny, T, B = 4, 2, 257, 5
+    cases = [lgssm_case(n, ny, T, seed=50) for _ in range(B)]
+    rng = np.random.RandomState(0)
+    ys = np.stack([c["ys"] + 0.1 * rng.randn(T, ny) for c in cases])
+    m0 = np.stack([c["m0"] + 0.1 * i for i, c in enumerate(cases)])
+    L0 = np.stack([c["L0"] for c in cases])
+    ssm = LinearizedSSM(*[_g(cases[0][k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")])
+    fm, fL, sm, sL, ell = _lib.filter_smoother(ssm, _g(ys), _g(m0), _g(L0), smooth=True, loglik=True)
+    for i in range(B):
+        c = dict(cases[0], ys=ys[i], m0=m0[i], L0=L0[i])
+        ofm, ofc, osm, osc, oell = oracle_from_ssm(c)
+        _check_traj(f"filtered[{i}]", fm[i], fL[i], ofm, ofc)
+        _check_traj(f"smoothed[{i}]", sm[i], sL[i], osm, osc)
+        assert abs(ell[i].item() - oell) <= TOL_ELL * abs(oell)
+
+
+@pytest.mark.parametrize("dim_x", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("seed", [0, 42])
+def test_filtering_operator(dim_x, seed):
+    """Known-answer generator of the reference's tests/test_parallel_operators.py:17-58, at 1e-9."""
+    from psqrt import _lib
+    np.random.seed(seed)
+    tri = lambda: np.tril(np.random.rand(dim_x, dim_x))
+    A1, A2 = np.random.randn(dim_x, dim_x), np.random.randn(dim_x, dim_x)
+    b1, b2 = np.random.randn(dim_x), np.random.randn(dim_x)
+    U1, U2 = tri(), tri()
+    eta1, eta2 = np.random.randn(dim_x), np.random.randn(dim_x)
+    Z1, Z2 = tri(), tri()
+    e1, e2 = (A1, b1, U1, eta1, Z1), (A2, b2, U2, eta2, Z2)
+    out = _lib.filter_combine([_g(a) for a in e1], [_g(a) for a in e2])
+    A, b, U, eta, Z = [o.cpu().numpy() for o in out]
+    oA, ob, oU, oeta, oZ = O.sqrt_filtering_operator(tuple(a[None] for a in e1), tuple(a[None] for a in e2))
+    sA, sb, sC, seta, sJ = O.standard_filtering_operator((A1, b1, U1 @ U1.T, eta1, Z1 @ Z1.T),
+                                                         (A2, b2, U2 @ U2.T, eta2, Z2 @ Z2.T))
+    for got, exp in ((A, oA[0]), (b, ob[0]), (eta, oeta[0]), (LLt(U), LLt(oU[0])), (LLt(Z), LLt(oZ[0]))):
+        assert rel_err(got, exp) < TOL
+    for got, exp in ((A, sA), (b, sb), (eta, seta), (LLt(U), sC), (LLt(Z), sJ)):   # sqrt == standard
+        assert rel_err(got, exp) < 1e-7
+
+
+@pytest.mark.parametrize("dim_x", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("seed", [0, 42])
+def test_smoothing_operator(dim_x, seed):
+    """tests/test_parallel_operators.py:61-89."""
+    from psqrt import _lib
+    np.random.seed(seed)
+    g1, g2 = np.random.randn(dim_x), np.random.randn(dim_x)
+    E1, E2 = np.random.randn(dim_x, dim_x), np.random.randn(dim_x, dim_x)
+    D1, D2 = np.tril(np.random.rand(dim_x, dim_x)), np.tril(np.random.rand(dim_x, dim_x))
+    out = _lib.smoother_combine([_g(a) for a in (g1, E1, D1)], [_g(a) for a in (g2, E2, D2)])
+    g, E, D = [o.cpu().numpy() for o in out]
+    og, oE, oD = O.sqrt_smoothing_operator((g1[None], E1[None], D1[None]), (g2[None], E2[None], D2[None]))
+    assert rel_err(g, og[0]) < TOL and rel_err(E, oE[0]) < TOL and rel_err(LLt(D), LLt(oD[0])) < TOL
+    sg, sE, sL = O.standard_smoothing_operator((g1, E1, D1 @ D1.T), (g2, E2, D2 @ D2.T))
+    assert rel_err(LLt(D), sL) < 1e-7
+
+
+@pytest.mark.parametrize("n,ny", [(1, 1), (2, 1), (3, 3), (4, 2), (5, 2), (1, 3), (2, 3), (8, 4)])
+def test_elements_and_scans(n, ny):
+    """The reference's own seams: element construction (parallel/_filtering.py:100-146,
+    _smoothing.py:47-85), the two associative scans, and the log-likelihood terms."""
+    from psqrt import _lib
+    T = 203
+    case = lgssm_case(n, ny, T, seed=11 * n + ny, triangular_prior=False)   # dense prior factor allowed here
+    ssm = _ssm(case)
+    ys = _g(case["ys"])
+    A, b, U, eta, Z = _lib.filter_elements(ssm, ys, _g(case["m0"]), _g(case["L0"]))
+    bc = lambda a, core: np.broadcast_to(a, (T,) + a.shape[-core:])
+    lin = (bc(case["F"], 2), bc(case["cholQ"], 2), bc(case["b"], 1), bc(case["H"], 2), bc(case["cholR"], 2),
+           bc(case["c"], 1))
+    ms = np.concatenate([case["m0"][None], np.zeros((T - 1, n))])
+    Ls = np.concatenate([case["L0"][None], np.zeros((T - 1, n, n))])
+    oel = O.sqrt_filtering_elements(*lin, ms, Ls, case["ys"])
+    for got, exp, is_factor in zip((A, b, U, eta, Z), oel, (0, 0, 1, 0, 1)):
+        got = got.cpu().numpy()
+        assert rel_err(LLt(got), LLt(exp)) < TOL if is_factor else rel_err(got, exp) < TOL
+    means, chols = _lib.filter_scan(A, b, U, eta, Z, chunk_len=3)
+    _, ofm, ofc, _, _ = O.associative_scan(O.sqrt_filtering_operator, oel)
+    _check_traj("filter_scan", means, chols, ofm, ofc)
+    fm = torch.cat([_g(case["m0"])[None], means])
+    fL = torch.cat([_lib.tria(_g(case["L0"]))[None], chols])
+    terms = _lib.loglik_terms(ssm, ys, fm, fL).cpu().numpy()
+    ofm1 = np.concatenate([case["m0"][None], ofm])
+    ofc1 = np.concatenate([case["L0"][None], ofc])
+    oterms = O.sqrt_loglikelihood_terms(*lin, ofm1[:-1], ofc1[:-1], case["ys"])
+    assert rel_err(terms, oterms) < TOL_ELL
+    g, E, D = _lib.smoother_elements(ssm, fm, fL)
+    og, oE, oD = O.sqrt_smoothing_elements(lin[0], lin[1], lin[2], ofm1[:-1], ofc1[:-1])
+    assert rel_err(g[:-1].cpu().numpy(), og) < TOL and rel_err(E[:-1].cpu().numpy(), oE) < TOL
+    assert rel_err(LLt(D[:-1].cpu().numpy()), LLt(oD)) < TOL
+    assert torch.equal(g[-1], fm[-1]) and float(E[-1].abs().max()) == 0.0
+    sm, sL = _lib.smoother_scan(g, E, D, chunk_len=2)
+    og = np.concatenate([og, ofm1[-1:]])
+    oE = np.concatenate([oE, np.zeros((1, n, n))])
+    oD = np.concatenate([oD, ofc1[-1:]])
+    osm, _, osc = O.associative_scan(O.sqrt_smoothing_operator, (og, oE, oD), reverse=True)
+    _check_traj("smoother_scan", sm, sL, osm, osc)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (2, 4), (3, 3), (4, 8), (5, 10), (5, 243), (6, 7), (8, 16), (2, 9)])
+def test_tria(rows, cols):
+    from psqrt import _lib
+    rng = np.random.RandomState(rows * 100 + cols)
+    A = rng.randn(37, rows, cols)
+    L = _lib.tria(_g(A)).cpu().numpy()
+    assert np.all(np.triu(L, 1) == 0)
+    assert rel_err(LLt(L), A @ np.swapaxes(A, -1, -2)) < 1e-12
+    assert rel_err(LLt(L), LLt(O.tria(A))) < 1e-12
+
+
+@pytest.mark.parametrize("multiplier", [1.0, -0.1])
+@pytest.mark.parametrize("dim_x", [2, 3, 5, 8])
+@pytest.mark.parametrize("seed", [0, 42, 666])
+def test_cholesky_update(multiplier, dim_x, seed):
+    """tests/test_math_utils.py:19-54 (update and update_many), plus the non-finite -> 0 guard."""
+    from psqrt import _lib
+    np.random.seed(seed)
+    B = 3
+    cholQ = np.tril(np.random.rand(dim_x, dim_x))
+    v = np.random.rand(B, dim_x)
+    expected = cholQ @ cholQ.T + multiplier * sum(v[k, :, None] @ v[k, None, :] for k in range(B))
+    got = _lib.chol_update_many(_g(cholQ), _g(v), multiplier).cpu().numpy()
+    ref = O.cholesky_update_many(cholQ, v, multiplier)
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-300, equal_nan=True)
+    if min(np.linalg.eigvals(expected).real) > 1e-6:
+        np.testing.assert_allclose(got @ got.T, expected, rtol=1e-4)
+    # downdate past positive-definiteness: NaNs are replaced by zeros exactly like _utils.py:80
+    bad = _lib.chol_update_many(_g(0.1 * cholQ), _g(10 * v), -1.0).cpu().numpy()
+    ref_bad = O.cholesky_update_many(0.1 * cholQ, 10 * v, -1.0)
+    assert np.all(np.isfinite(bad))
+    np.testing.assert_allclose(bad, ref_bad, rtol=1e-10, atol=1e-300)
+
+
+def _torch_models(case):
+    import psqrt
+    from psqrt.models import lgssm
+    tm = psqrt.FunctionalModel(lgssm.transition_function(case["F"]), psqrt.MVNSqrt(_g(case["b"]), _g(case["cholQ"])))
+    om = psqrt.FunctionalModel(lgssm.observation_function(case["H"]), psqrt.MVNSqrt(_g(case["c"]), _g(case["cholR"])))
+    return tm, om
+
+
+@pytest.mark.parametrize("dim_x,dim_y", [(1, 1), (2, 1), (3, 2), (2, 3), (4, 2)])
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+def test_methods_api_lgssm(dim_x, dim_y, lin_name):
+    """methods.filtering / smoothing / filter_smoother / iterated_smoothing through the public API,
+    mirroring tests/test_parallel_filter.py:80-122, test_parallel_smoother.py:61-99 and
+    test_iterated_smoother.py:31-69 (explicit random nominal trajectory, linear model)."""
+    import psqrt
+    T = 25
+    case = lgssm_case(dim_x, dim_y, T, seed=dim_x * 10 + dim_y)
+    rng = np.random.RandomState(5)
+    nominal_np = O.MVNSqrt(rng.randn(T + 1, dim_x), np.repeat(np.eye(dim_x)[None], T + 1, 0))
+    nominal = psqrt.MVNSqrt(_g(nominal_np.mean), _g(nominal_np.chol))
+    lin = getattr(psqrt.linearization, lin_name)
+    olin = getattr(O, lin_name)
+    tm, om = _torch_models(case)
+    otm, oom = oracle_lgssm_models(case)
+    x0 = psqrt.MVNSqrt(_g(case["m0"]), _g(case["L0"]))
+    ox0 = O.MVNSqrt(case["m0"], case["L0"])
+    filt, ell = psqrt.filtering(case["ys"], x0, tm, om, lin, nominal, True, return_loglikelihood=True)
+    ofilt, oell = O.par_filtering(case["ys"], ox0, otm, oom, olin, nominal_np, True)
+    _check_traj("filtering", filt.mean, filt.chol, ofilt.mean, ofilt.chol)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+    sfilt, sell = O.seq_filtering(case["ys"], ox0, otm, oom, olin, nominal_np, True)
+    _check_traj("filtering-vs-seq", filt.mean, filt.chol, sfilt.mean, sfilt.chol)
+    assert torch.equal(filt.mean[0], x0.mean) and torch.equal(filt.chol[0], x0.chol)
+    smo = psqrt.smoothing(tm, filt, lin, nominal, True)
+    osmo = O.par_smoothing(otm, ofilt, olin, nominal_np)
+    _check_traj("smoothing", smo.mean, smo.chol, osmo.mean, osmo.chol)
+    fs = psqrt.filter_smoother(case["ys"], x0, tm, om, lin, nominal, True)
+    _check_traj("filter_smoother", fs.mean, fs.chol, osmo.mean, osmo.chol)
+    it = psqrt.iterated_smoothing(case["ys"], x0, tm, om, lin, nominal, True, criterion=lambda i, *_: i < 5)
+    oseq = O.seq_smoothing(otm, O.seq_filtering(case["ys"], ox0, otm, oom, olin, nominal_np), olin, nominal_np)
+    _check_traj("iterated", it.mean, it.chol, oseq.mean, oseq.chol, tol=1e-8)
+    # default nominal (None) and default criterion
+    it2, ell2 = psqrt.iterated_smoothing(case["ys"], x0, tm, om, lin, None, True, return_loglikelihood=True)
+    oit2, oell2 = O.iterated_smoothing(case["ys"], ox0, otm, oom, olin, None, True, return_loglikelihood=True)
+    _check_traj("iterated-default", it2.mean, it2.chol, oit2.mean, oit2.chol, tol=1e-8)
+    assert abs(ell2.item() - oell2) <= TOL_ELL * abs(oell2)
+
+
+def _bearings_setup(T, seed=0):
+    from psqrt.models import bearings
+    s1, s2, r, dt, qc, qw = np.array([-1.5, 0.5]), np.array([1.0, 1.0]), 0.5, 0.01, 0.01, 0.1
+    _, _, ys = bearings.get_data(np.array([0.1, 0.2, 1.0, 0.0]), dt, r, T, s1, s2, random_state=seed)
+    ys = ys.astype(np.float64)
+    Q, R, obs_f, trans_f = bearings.make_parameters(qc, qw, r, dt, s1, s2)
+    oQ, oR, oobs, otrans = O.bearings_make_parameters(qc, qw, r, dt, s1, s2)
+    cholQ, cholR = np.linalg.cholesky(Q), np.linalg.cholesky(R)
+    m0 = np.array([-4.0, -1.0, 2.0, 7.0, 3.0])
+    return ys, m0, cholQ, cholR, (obs_f, trans_f), (oobs, otrans)
+
+
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+def test_bearings_iterated_smoother(lin_name):
+    """Config 2/3 shape at test size: coordinated-turn + 2 bearings, nx=5, iterated sqrt parallel
+    smoother from the notebooks' initial nominal, 10 iterations, + log-likelihood."""
+    import psqrt
+    T = 500
+    ys, m0, cholQ, cholR, (obs_f, trans_f), (oobs, otrans) = _bearings_setup(T)
+    lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+    x0 = psqrt.MVNSqrt(_g(m0), _g(np.eye(5)))
+    tm = psqrt.FunctionalModel(trans_f, psqrt.MVNSqrt(_g(np.zeros(5)), _g(cholQ)))
+    om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(_g(np.zeros(2)), _g(cholR)))
+    otm = O.FunctionalModel(otrans, O.MVNSqrt(np.zeros(5), cholQ))
+    oom = O.FunctionalModel(oobs, O.MVNSqrt(np.zeros(2), cholR))
+    nom_m = np.tile(np.array([-1.0, -1.0, 6.0, 4.0, 2.0]), (T + 1, 1))
+    nom_L = np.repeat(np.eye(5)[None], T + 1, 0)
+    n_iter = 10
+    res, ell = psqrt.iterated_smoothing(ys, x0, tm, om, lin, psqrt.MVNSqrt(_g(nom_m), _g(nom_L)), True,
+                                        criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)
+    ores, oell = O.iterated_smoothing(ys, O.MVNSqrt(m0, np.eye(5)), otm, oom, olin, O.MVNSqrt(nom_m, nom_L), True,
+                                      criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)
+    # 10 nonlinear iterations amplify rounding differences; the contract is per pass, so also check one pass
+    _check_traj("iterated", res.mean, res.chol, ores.mean, ores.chol, tol=1e-7)
+    assert abs(ell.item() - oell) <= 1e-7 * abs(oell)
+    one = psqrt.filter_smoother(ys, x0, tm, om, lin, psqrt.MVNSqrt(_g(ores.mean), _g(ores.chol)), True)
+    oone = O.filter_smoother(ys, O.MVNSqrt(m0, np.eye(5)), otm, oom, olin, ores, True)
+    _check_traj("one pass at the oracle's nominal", one.mean, one.chol, oone.mean, oone.chol)
+
+
+def test_population_model():
+    """Config 5b: Ricker / Poisson conditional-moments model, nx = ny = 1, sqrt path
+    (notebooks/population_model.py; experiment-poisson.ipynb: lam = 10, Q = 0.09, x0 = log 7)."""
+    import psqrt
+    from psqrt.models import population
+    T = 129
+    lam, Q = 10.0, np.array([[0.09]])
+    _, ys = population.get_data(np.log(7.0), T, Q, lam, random_state=0)
+    tmod, omod = population.make_parameters(lam, Q)
+    otmod, oomod = O.population_model(lam, Q)
+    x0 = psqrt.MVNSqrt(_g(np.array([np.log(7.0)])), _g(np.eye(1)))
+    ox0 = O.MVNSqrt(np.array([np.log(7.0)]), np.eye(1))
+    nom_m = np.full((T + 1, 1), np.log(7.0))
+    nom_L = np.repeat(np.eye(1)[None], T + 1, 0)
+    for lin_name in ("extended", "cubature", "gauss_hermite"):
+        lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+        res = psqrt.iterated_smoothing(ys, x0, tmod, omod, lin, psqrt.MVNSqrt(_g(nom_m), _g(nom_L)), True,
+                                       criterion=lambda i, *_: i < 5)
+        ores = O.iterated_smoothing(ys, ox0, otmod, oomod, olin, O.MVNSqrt(nom_m, nom_L), True,
+                                    criterion=lambda i, *_: i < 5)
+        _check_traj(f"population/{lin_name}", res.mean, res.chol, ores.mean, ores.chol, tol=1e-8)
+
+
+def test_user_supplied_torch_model():
+    """A model the library does not know: plain torch callables differentiated with torch.func
+    (the 'user-supplied models still linearise on the host side and feed the CUDA scan' seam)."""
+    import psqrt
+    T = 200
+    rng = np.random.RandomState(1)
+    ys = rng.randn(T, 1)
+
+    def f(x):
+        return torch.stack([x[0] + 0.1 * torch.sin(x[1]), 0.9 * x[1] + 0.05 * torch.cos(x[0])])
+
+    def h(x):
+        return torch.stack([torch.sqrt(1.0 + x[0] ** 2 + x[1] ** 2)])
+
+    def f_np(x):
+        return np.stack([x[..., 0] + 0.1 * np.sin(x[..., 1]), 0.9 * x[..., 1] + 0.05 * np.cos(x[..., 0])], -1)
+
+    def f_jac(x):
+        J = np.zeros(x.shape[:-1] + (2, 2))
+        J[..., 0, 0], J[..., 0, 1] = 1.0, 0.1 * np.cos(x[..., 1])
+        J[..., 1, 0], J[..., 1, 1] = -0.05 * np.sin(x[..., 0]), 0.9
+        return J
+
+    f_np.jac = f_jac
+
+    def h_np(x):
+        return np.sqrt(1.0 + x[..., 0] ** 2 + x[..., 1] ** 2)[..., None]
+
+    h_np.jac = lambda x: (x / np.sqrt(1.0 + x[..., 0] ** 2 + x[..., 1] ** 2)[..., None])[..., None, :]
+    cQ, cR = 0.3 * np.eye(2), 0.5 * np.eye(1)
+    x0 = psqrt.MVNSqrt(_g(np.array([0.5, -0.2])), _g(np.eye(2)))
+    tm = psqrt.FunctionalModel(f, psqrt.MVNSqrt(_g(np.zeros(2)), _g(cQ)))
+    om = psqrt.FunctionalModel(h, psqrt.MVNSqrt(_g(np.zeros(1)), _g(cR)))
+    otm = O.FunctionalModel(f_np, O.MVNSqrt(np.zeros(2), cQ))
+    oom = O.FunctionalModel(h_np, O.MVNSqrt(np.zeros(1), cR))
+    for lin_name in ("extended", "cubature"):
+        lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+        res = psqrt.iterated_smoothing(ys, x0, tm, om, lin, None, True, criterion=lambda i, *_: i < 3)
+        ores = O.iterated_smoothing(ys, O.MVNSqrt(np.array([0.5, -0.2]), np.eye(2)), otm, oom, olin, None, True,
+                                    criterion=lambda i, *_: i < 3)
+        _check_traj(f"user/{lin_name}", res.mean, res.chol, ores.mean, ores.chol, tol=1e-8)
+
+
+def test_reference_golden_bearings():
+    """The reference's only stored goldens (tests/test_bearings_only.py:23-72): 100-iteration ICKS on
+    tests/bearings/ys.npy, produced upstream by a float32 run and compared there at 3 decimals."""
+    import os
+    import psqrt
+    from psqrt.models import bearings
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    ys = np.load(os.path.join(gold, "bearings_ys.npy")).astype(np.float64)
+    with np.load(os.path.join(gold, "bearings_icks.npz")) as z:
+        exp_m, exp_P = z["arr_0"], z["arr_1"]
+    Q, R, obs_f, trans_f = bearings.make_parameters(0.01, 0.1, 0.5, 0.01, np.array([-1.5, 0.5]), np.array([1.0, 1.0]))
+    x0 = psqrt.MVNSqrt(_g(np.array([-1.0, -1.0, 0.0, 0.0, 0.0])), _g(np.eye(5)))
+    tm = psqrt.FunctionalModel(trans_f, psqrt.MVNSqrt(_g(np.zeros(5)), _g(np.linalg.cholesky(Q))))
+    om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(_g(np.zeros(2)), _g(np.linalg.cholesky(R))))
+    res = psqrt.iterated_smoothing(ys, x0, tm, om, psqrt.linearization.cubature, None, True,
+                                   criterion=lambda i, *_: i < 100)
+    m = res.mean.cpu().numpy()[1:]
+    P = LLt(res.chol.cpu().numpy())[1:]
+    np.testing.assert_array_almost_equal(m, exp_m, decimal=3)
+    np.testing.assert_array_almost_equal(P, exp_P, decimal=3)
+
+
+def test_full_size_properties():
+    """BASELINE size (T = 1e6, nx = 4) through size-independent properties: (1) the pass is
+    invariant to the chunking (two different chunk lengths = two different association orders);
+    (2) its first 20 000 steps agree with the oracle filter; (3) the last smoothed state equals the
+    last filtered state; (4) smoothed factors never exceed filtered ones in trace."""
+    from psqrt import _lib
+    T = 1_000_000
+    case = lgssm_case(4, 2, 20_000, seed=0)
+    rng = np.random.RandomState(1)
+    ys = np.concatenate([case["ys"], rng.randn(T - 20_000, 2)])
+    ssm = _ssm(case)
+    a = _lib.filter_smoother(ssm, _g(ys), _g(case["m0"]), _g(case["L0"]), smooth=True, loglik=True)
+    b = _lib.filter_smoother(ssm, _g(ys), _g(case["m0"]), _g(case["L0"]), smooth=True, loglik=True, chunk_len=61)
+    for i, name in ((0, "fm"), (2, "sm")):
+        assert rel_err(a[i].cpu().numpy(), b[i].cpu().numpy()) < TOL, name
+    for i, name in ((1, "fL"), (3, "sL")):
+        assert rel_err(LLt(a[i].cpu().numpy()), LLt(b[i].cpu().numpy())) < TOL, name
+    assert abs(a[4].item() - b[4].item()) <= TOL_ELL * abs(b[4].item())
+    ofm, ofc, _, _, _ = oracle_from_ssm(case)
+    _check_traj("prefix", a[0][:20_001], a[1][:20_001], ofm, ofc)
+    assert torch.equal(a[2][-1], a[0][-1])
+    tr_f = (a[1] ** 2).sum((-1, -2))
+    tr_s = (a[3] ** 2).sum((-1, -2))
+    assert bool((tr_s <= tr_f * (1 + 1e-9)).all())
