@@ -23,7 +23,10 @@ BUILD = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "psqrt", "libpsqrt.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-NX_LIST = (1, 2, 3, 4, 5, 6, 8)   # compiled state dimensions
+ALL_NX = (1, 2, 3, 4, 5, 6, 8)    # state dimensions the dispatcher knows (psqrt_capi.cu)
+# compiled state dimensions; PSQRT_NX_LIST="4,5" builds a development subset (the others then
+# report PSQRT_EUNSUPPORTED at run time)
+NX_LIST = tuple(int(v) for v in os.environ.get("PSQRT_NX_LIST", "").split(",") if v) or ALL_NX
 MAX_NY = 4                        # observation dimensions 1..MAX_NY for each of them
 
 NVCC_FLAGS = [
@@ -64,15 +67,17 @@ def _compile(args):
 def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
     tag = _digest(f"{NX_LIST}{MAX_NY}")
-    stamp = os.path.join(BUILD, "stamp.txt")
+    stamp = OUT + ".stamp"
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == tag:
         if verbose:
             print(f"[psqrt build] up to date: {OUT}")
         return OUT
     units = []
-    for n in NX_LIST:
-        units.append((os.path.join(CSRC, "psqrt_inst.cu"), os.path.join(BUILD, f"inst_n{n}_{tag}.o"),
-                      [f"-DPSQ_N={n}", f"-DPSQ_MAX_NY={MAX_NY}"]))
+    for n in ALL_NX:
+        defs = [f"-DPSQ_N={n}", f"-DPSQ_MAX_NY={MAX_NY}"]
+        if n not in NX_LIST:
+            defs.append("-DPSQ_STUB")       # launch table symbol only, no kernels
+        units.append((os.path.join(CSRC, "psqrt_inst.cu"), os.path.join(BUILD, f"inst_n{n}_{tag}.o"), defs))
     units.append((os.path.join(CSRC, "psqrt_capi.cu"), os.path.join(BUILD, f"capi_{tag}.o"), []))
     if os.path.exists(os.path.join(CSRC, "psqrt_models.cu")):
         units.append((os.path.join(CSRC, "psqrt_models.cu"), os.path.join(BUILD, f"models_{tag}.o"), []))

@@ -8,6 +8,12 @@
 #include "psqrt_kernels.cuh"
 #include "psqrt_launch.h"
 
+namespace psq {
+void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
+  k_ell_sum<0><<<(unsigned)B, 256, 0, st>>>(ell_part, M, ell_out);
+}
+}  // namespace psq
+
 namespace {
 
 using psq::LaunchN;

@@ -1,6 +1,5 @@
 // psqrt_inst.cu -- instantiates every kernel for ONE state dimension (compile with
 // -DPSQ_N=<nx>); observation dimensions 1..PSQ_MAX_NY are instantiated for that nx.
-#include "psqrt_kernels.cuh"
 #include "psqrt_launch.h"
 
 #ifndef PSQ_N
@@ -9,6 +8,17 @@
 #ifndef PSQ_MAX_NY
 #define PSQ_MAX_NY 4
 #endif
+
+#define PSQ_CAT_(a, b) a##b
+#define PSQ_CAT(a, b) PSQ_CAT_(a, b)
+
+#ifdef PSQ_STUB
+// development builds (PSQRT_NX_LIST): this state dimension is not compiled in
+namespace psq {
+const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
+}
+#else
+#include "psqrt_kernels.cuh"
 
 namespace psq {
 namespace {
@@ -158,14 +168,8 @@ const LaunchN kTable = {N,
 
 }  // namespace
 
-#define PSQ_CAT_(a, b) a##b
-#define PSQ_CAT(a, b) PSQ_CAT_(a, b)
 const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return &kTable; }
 
-#if PSQ_N == 1
-void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
-  k_ell_sum<0><<<(unsigned)B, 256, 0, st>>>(ell_part, M, ell_out);
-}
-#endif
 
 }  // namespace psq
+#endif  // PSQ_STUB

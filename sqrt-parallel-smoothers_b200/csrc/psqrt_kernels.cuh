@@ -469,9 +469,23 @@ __global__ void k_loglik_terms(SSMArgs a, long long T, long long B, const double
 }
 
 // Generic element scans: inputs are reference-layout dense arrays (AoS per step).
+// Square-root factors arriving through the element-level seams may be ANY n x n factor (the
+// reference's raw elements carry Z = [Z0 | 0], parallel/_filtering.py:141-142, which is not
+// triangular): they are triangularised on load, which leaves F F^T unchanged.
+template <int N>
+__device__ __forceinline__ void load_factor_tria(const double* M, double (&Lw)[N][N]) {
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int q = 0; q < N; ++q) Lw[r][q] = M[r * N + q];
+  house_rows<N, N, N - 1>(Lw);
+}
 template <int N>
 __device__ __forceinline__ void load_felem_dense(const double* A, const double* b, const double* U, const double* eta,
                                                  const double* Z, long long i, FElem<N>& e) {
+  double Uw[N][N], Zw[N][N];
+  load_factor_tria<N>(U + i * N * N, Uw);
+  load_factor_tria<N>(Z + i * N * N, Zw);
 #pragma unroll
   for (int r = 0; r < N; ++r) {
     e.b(r) = b[i * N + r];
@@ -480,21 +494,23 @@ __device__ __forceinline__ void load_felem_dense(const double* A, const double* 
     for (int q = 0; q < N; ++q) e.A(r, q) = A[i * N * N + r * N + q];
 #pragma unroll
     for (int q = 0; q <= r; ++q) {
-      e.U(r, q) = U[i * N * N + r * N + q];
-      e.Z(r, q) = Z[i * N * N + r * N + q];
+      e.U(r, q) = Uw[r][q];
+      e.Z(r, q) = Zw[r][q];
     }
   }
 }
 template <int N>
 __device__ __forceinline__ void load_selem_dense(const double* g, const double* E, const double* D, long long i,
                                                  SElem<N>& e) {
+  double Dw[N][N];
+  load_factor_tria<N>(D + i * N * N, Dw);
 #pragma unroll
   for (int r = 0; r < N; ++r) {
     e.g(r) = g[i * N + r];
 #pragma unroll
     for (int q = 0; q < N; ++q) e.E(r, q) = E[i * N * N + r * N + q];
 #pragma unroll
-    for (int q = 0; q <= r; ++q) e.D(r, q) = D[i * N * N + r * N + q];
+    for (int q = 0; q <= r; ++q) e.D(r, q) = Dw[r][q];
   }
 }
 
