@@ -236,7 +236,7 @@ def run_psqrt(args):
             return sharded.filter_smoother(ssm, ys[None], m0[None], L0[None])
     else:
         def one_pass():
-            return _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=False)
+            return _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=False, chunk_len=args.chunk)
 
     def barrier():
         if world > 1:
@@ -315,11 +315,11 @@ def run_psqrt(args):
         for it in range(3 + 10):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            _lib.filter_reduce(ssm, yb, NX)
+            _lib.filter_reduce(ssm, yb, NX, chunk_len=args.chunk)
             ev[1].record()
-            fm, fL, _, stot = _lib.filter_apply(ssm, yb, m0b, L0b, smooth=True, loglik=False)
+            fm, fL, _, stot = _lib.filter_apply(ssm, yb, m0b, L0b, smooth=True, loglik=False, chunk_len=args.chunk)
             ev[2].record()
-            _lib.smoother_apply(ssm, fm, fL, fm[:, -1].contiguous(), fL[:, -1].contiguous())
+            _lib.smoother_apply(ssm, fm, fL, fm[:, -1].contiguous(), fL[:, -1].contiguous(), chunk_len=args.chunk)
             ev[3].record()
             torch.cuda.synchronize()
             if it >= 3:
@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="psqrt", choices=["psqrt", "reference"])
     ap.add_argument("--T", type=int, default=T_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="chunk length override (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -29,7 +29,9 @@ ALL_NX = (1, 2, 3, 4, 5, 6, 8)    # state dimensions the dispatcher knows (psqrt
 NX_LIST = tuple(int(v) for v in os.environ.get("PSQRT_NX_LIST", "").split(",") if v) or ALL_NX
 MAX_NY = 4                        # observation dimensions 1..MAX_NY for each of them
 
-NVCC_FLAGS = [
+EXTRA = [f for f in os.environ.get("PSQRT_NVCC_EXTRA", "").split() if f]
+OUT = os.environ.get("PSQRT_OUT", OUT)
+NVCC_FLAGS = EXTRA + [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]

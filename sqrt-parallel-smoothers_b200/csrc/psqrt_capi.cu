@@ -64,7 +64,8 @@ int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_
 // Workspace carving (doubles).  One layout serves the fused pass, the staged calls and the
 // element scans, so a workspace sized for the op can be reused across stages.
 struct Ws {
-  double *chunk_pref, *warp_tot, *ftotal, *chunk_suf, *warp_stot, *stotal, *ell_part, *ell_tmp;
+  double *chunk_pref, *warp_tot, *group_f, *ftotal, *chunk_suf, *warp_stot, *group_s, *stotal, *ell_part, *ell_tmp;
+  unsigned int *counter_f, *counter_s;
   size_t doubles;
 };
 Ws carve(void* base, const psqrt_plan& p, int64_t B) {
@@ -77,13 +78,18 @@ Ws carve(void* base, const psqrt_plan& p, int64_t B) {
     return r;
   };
   w.chunk_pref = take((size_t)B * p.nf_filter * p.n_chunks_pad);
+  const size_t G = (size_t)(p.n_warps + 31) / 32;
   w.warp_tot = take((size_t)B * p.nf_filter * p.n_warps);
+  w.group_f = take((size_t)B * p.nf_filter * G);
   w.ftotal = take((size_t)B * p.nf_filter);
   w.chunk_suf = take((size_t)B * p.nf_smoother * p.n_chunks_pad);
   w.warp_stot = take((size_t)B * p.nf_smoother * p.n_warps);
+  w.group_s = take((size_t)B * p.nf_smoother * G);
   w.stotal = take((size_t)B * p.nf_smoother);
   w.ell_part = take((size_t)B * p.n_warps);
   w.ell_tmp = take((size_t)B);
+  w.counter_f = (unsigned int*)take((size_t)B);   // one 8-byte slot per sequence, used as uint32
+  w.counter_s = (unsigned int*)take((size_t)B);
   w.doubles = off;
   return w;
 }
@@ -178,8 +184,10 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
-  c.lny->filter_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot, st);
-  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, ftotal ? ftotal : c.ws.ftotal, st);
+  c.lny->filter_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot,
+                       c.ws.counter_f, st);
+  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, ftotal ? ftotal : c.ws.ftotal,
+                   st);
   return check_launch();
 }
 
@@ -203,9 +211,11 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   SSMArgs a = make_args(ssm, y, ny, T);
   const int smooth = stotal != nullptr;
   c.lny->filter_apply(smooth, a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, c.ws.chunk_pref,
-                      c.ws.warp_tot, fm, fL, c.ws.chunk_suf, c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, st);
+                      c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
+                      ell ? c.ws.ell_part : nullptr, c.ws.counter_s, st);
   if (smooth) {
-    c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, stotal, ell ? c.ws.ell_part : nullptr, ell, st);
+    c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, stotal,
+                     ell ? c.ws.ell_part : nullptr, ell, st);
   } else if (ell) {
     psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
   }
@@ -232,7 +242,8 @@ int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* f
   if (rc) return rc;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
   c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, nx, (long long)nx * nx,
-                     c.ws.chunk_suf, c.ws.warp_stot, fm, fL, sm, sL, write_terminal, (cudaStream_t)stream);
+                     c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, write_terminal,
+                     (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -253,7 +264,7 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
   SSMArgs a = make_args(ssm, nullptr, 0, T);
   c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
                      fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
-                     c.ws.warp_stot, fm, fL, sm, sL, 1, (cudaStream_t)stream);
+                     c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, 1, (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -265,11 +276,13 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
-  c.ln->smooth_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot, st);
-  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.stotal, nullptr, nullptr, st);
+  c.ln->smooth_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
+                      c.ws.counter_s, st);
+  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
+                   st);
   c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
                      fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
-                     c.ws.warp_stot, fm, fL, sm, sL, 1, st);
+                     c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, 1, st);
   return check_launch();
 }
 
@@ -294,10 +307,10 @@ int psqrt_filter_scan(const double* A, const double* b, const double* U, const d
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c.ln->escan_filter_reduce(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
-                            c.ws.warp_tot, st);
-  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.ftotal, st);
+                            c.ws.warp_tot, c.ws.counter_f, st);
+  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, c.ws.ftotal, st);
   c.ln->escan_filter_apply(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
-                           c.ws.warp_tot, means, chols, st);
+                           c.ws.warp_tot, c.ws.group_f, means, chols, st);
   return check_launch();
 }
 
@@ -318,10 +331,11 @@ int psqrt_smoother_scan(const double* g, const double* E, const double* D, int n
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c.ln->escan_smooth_reduce(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
-                            st);
-  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.stotal, nullptr, nullptr, st);
+                            c.ws.counter_s, st);
+  c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
+                   st);
   c.ln->escan_smooth_apply(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
-                           means, chols, st);
+                           c.ws.group_s, means, chols, st);
   return check_launch();
 }
 

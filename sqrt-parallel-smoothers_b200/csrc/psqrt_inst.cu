@@ -31,20 +31,19 @@ inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)
 template <int NY>
 struct NYImpl {
   static void filter_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, double* chunk_pref,
-                            double* warp_tot, cudaStream_t st) {
-    k_filter_reduce<N, NY><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, chunk_pref, warp_tot);
+                            double* warp_tot, unsigned int* counter, cudaStream_t st) {
+    k_filter_reduce<N, NY><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, chunk_pref, warp_tot, counter);
   }
   static void filter_apply(int smooth, const SSMArgs& a, long long T, int K, long long Ppad, long long B,
                            const double* cm, const double* cL, const double* chunk_pref, const double* warp_pref,
-                           double* fm, double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
-                           cudaStream_t st) {
+                           const double* group_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
+                           double* ell_part, unsigned int* counter_s, cudaStream_t st) {
     if (smooth)
-      k_filter_apply<N, NY, true><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, chunk_pref, warp_pref,
-                                                                        fm, fL, chunk_suf, warp_stot, ell_part);
+      k_filter_apply<N, NY, true><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
+          a, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s);
     else
-      k_filter_apply<N, NY, false><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, chunk_pref,
-                                                                         warp_pref, fm, fL, chunk_suf, warp_stot,
-                                                                         ell_part);
+      k_filter_apply<N, NY, false><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
+          a, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s);
   }
   static void filter_elements(const SSMArgs& a, long long T, long long B, const double* m0, const double* L0,
                               double* A, double* b, double* U, double* eta, double* Z, cudaStream_t st) {
@@ -76,25 +75,28 @@ const LaunchNY* for_ny(int ny) {
   }
 }
 
-template <class Elem>
-constexpr size_t mid_smem() { return (32 * Elem::NF + 32) * sizeof(double); }
+inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31) / 32), (unsigned)B, 1); }
 
-void mid_filter(double* items, long long M, long long B, double* total, cudaStream_t st) {
-  k_mid_scan<FElem<N>, false><<<(unsigned)B, kMidBlock, mid_smem<FElem<N>>(), st>>>(items, M, total, nullptr, nullptr);
-}
-void mid_smooth(double* items, long long M, long long B, double* total, const double* ell_part, double* ell_out,
+void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 cudaStream_t st) {
-  k_mid_scan<SElem<N>, true><<<(unsigned)B, kMidBlock, mid_smem<SElem<N>>(), st>>>(items, M, total, ell_part, ell_out);
+  k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, nullptr,
+                                                           nullptr);
+}
+void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                const double* ell_part, double* ell_out, cudaStream_t st) {
+  k_mid_scan<SElem<N>, true><<<mid_grid(M, B), 32, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, ell_part,
+                                                          ell_out);
 }
 void smooth_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* fm,
-                   const double* fL, double* chunk_suf, double* warp_stot, cudaStream_t st) {
-  k_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, fm, fL, chunk_suf, warp_stot);
+                   const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t st) {
+  k_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, fm, fL, chunk_suf, warp_stot, counter);
 }
 void smooth_apply(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* cm,
                   const double* cL, long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
-                  const double* fm, const double* fL, double* sm, double* sL, int write_terminal, cudaStream_t st) {
-  k_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, fm,
-                                                           fL, sm, sL, write_terminal);
+                  const double* group_suf, const double* fm, const double* fL, double* sm, double* sL,
+                  int write_terminal, cudaStream_t st) {
+  k_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf,
+                                                           group_suf, fm, fL, sm, sL, write_terminal);
 }
 void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                   double* cL, cudaStream_t st) {
@@ -110,24 +112,25 @@ void smoother_elements(const SSMArgs& a, long long T, long long B, const double*
 }
 void escan_filter_reduce(const double* A, const double* b, const double* U, const double* eta, const double* Z,
                          long long T, int K, long long Ppad, long long B, double* chunk_pref, double* warp_tot,
-                         cudaStream_t st) {
-  k_escan_filter_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(A, b, U, eta, Z, T, K, Ppad, chunk_pref, warp_tot);
+                         unsigned int* counter, cudaStream_t st) {
+  k_escan_filter_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(A, b, U, eta, Z, T, K, Ppad, chunk_pref, warp_tot,
+                                                                  counter);
 }
 void escan_filter_apply(const double* A, const double* b, const double* U, const double* eta, const double* Z,
                         long long T, int K, long long Ppad, long long B, const double* chunk_pref,
-                        const double* warp_pref, double* om, double* oL, cudaStream_t st) {
+                        const double* warp_pref, const double* group_pref, double* om, double* oL, cudaStream_t st) {
   k_escan_filter_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(A, b, U, eta, Z, T, K, Ppad, nullptr, nullptr,
-                                                                 chunk_pref, warp_pref, om, oL);
+                                                                 chunk_pref, warp_pref, group_pref, om, oL);
 }
 void escan_smooth_reduce(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
-                         long long B, double* chunk_suf, double* warp_stot, cudaStream_t st) {
-  k_escan_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(g, E, D, T, K, Ppad, chunk_suf, warp_stot);
+                         long long B, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t st) {
+  k_escan_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(g, E, D, T, K, Ppad, chunk_suf, warp_stot, counter);
 }
 void escan_smooth_apply(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
-                        long long B, const double* chunk_suf, const double* warp_suf, double* om, double* oL,
-                        cudaStream_t st) {
+                        long long B, const double* chunk_suf, const double* warp_suf, const double* group_suf,
+                        double* om, double* oL, cudaStream_t st) {
   k_escan_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(g, E, D, T, K, Ppad, nullptr, nullptr, chunk_suf,
-                                                                 warp_suf, om, oL);
+                                                                 warp_suf, group_suf, om, oL);
 }
 void filter_combine(const double* A1, const double* b1, const double* U1, const double* e1, const double* Z1,
                     const double* A2, const double* b2, const double* U2, const double* e2, const double* Z2,

@@ -25,8 +25,18 @@
 namespace psq {
 
 constexpr int kBlock = 128;      // threads per CTA in the sweeps (4 warps)
-constexpr int kMidBlock = 256;   // threads of the single mid-scan CTA (255 regs/thread available)
 constexpr unsigned kFull = 0xffffffffu;
+// minimum resident CTAs per SM requested from ptxas for the three sweeps (register cap =
+// 65536 / (128 * MINB)); tuned on B200, see DESIGN.md section 5
+#ifndef PSQ_MINB_K1
+#define PSQ_MINB_K1 2
+#endif
+#ifndef PSQ_MINB_K3
+#define PSQ_MINB_K3 2
+#endif
+#ifndef PSQ_MINB_K5
+#define PSQ_MINB_K5 2
+#endif
 
 // Linearised SSM as the kernels see it: base pointers + per-step and per-sequence strides in
 // doubles (0 = shared by all steps / all sequences).
@@ -133,12 +143,13 @@ __device__ __forceinline__ void store_gauss_dense(double* m, double* L, const Ga
 // K1
 // =========================================================================================
 template <int N, int NY>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K1)
 k_filter_reduce(SSMArgs a, long long T, int K, long long Ppad, double* __restrict__ chunk_pref,
-                double* __restrict__ warp_tot) {
+                double* __restrict__ warp_tot, unsigned int* __restrict__ counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (c == 0) counter[seq] = 0u;  // arms the ticket of the mid-level scan that follows
   FElem<N> acc;
   acc.set_identity();
   const long long k0 = c * K;
@@ -155,96 +166,93 @@ k_filter_reduce(SSMArgs a, long long T, int K, long long Ppad, double* __restric
 }
 
 // =========================================================================================
-// K2 / K4: exclusive scan of M items by one CTA per sequence (items in place -> exclusive
-// prefixes in scan order; total written to total_out[seq][NF]).  REV mirrors the index.
-// Optionally sums ell partials (deterministic order) into ell_out[seq].
+// K2 / K4: exclusive scan of the M warp totals of one sequence, two levels in one launch.
+//   level B: one single-warp CTA per group of 32 items (spread over the SMs): Kogge-Stone scan,
+//            in-group exclusive prefixes written in place, group total to groups[].
+//   level C: the CTA that finishes last (atomic ticket) scans the G = ceil(M / 32) group totals in
+//            place (exclusive), writes the sequence total and (optionally) the fixed-order sum of
+//            the log-likelihood partials, and re-arms the ticket counter.
+// REV mirrors the item index (suffix scan); groups[] is indexed in scan order.
+// The counter must be zero on entry: the reduce kernel that produced the items zeroes it.
 // =========================================================================================
-template <class Elem, bool REV>
-__global__ void __launch_bounds__(kMidBlock)
-k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ total_out,
-           const double* __restrict__ ell_part, double* __restrict__ ell_out) {
-  extern __shared__ double smem[];  // [32][NF] warp totals, then [32] ell
-  const long long seq = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long q = (M + kMidBlock - 1) / kMidBlock;
-  const long long s0 = (long long)tid * q;
-  const long long s1 = (s0 + q < M) ? s0 + q : M;
+template <class Elem>
+__device__ __forceinline__ void soa_load_cg(const double* buf, long long seq, long long n_items, long long i, Elem& e) {
+  const double* p = buf + seq * Elem::NF * n_items + i;
+#pragma unroll
+  for (int f = 0; f < Elem::NF; ++f) e.v[f] = __ldcg(p + f * n_items);
+}
 
+template <class Elem, bool REV>
+__global__ void __launch_bounds__(32)
+k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ groups, long long G,
+           unsigned int* __restrict__ counter, double* __restrict__ total_out,
+           const double* __restrict__ ell_part, double* __restrict__ ell_out) {
+  const long long seq = blockIdx.y;
+  const long long g = blockIdx.x;
+  const int lane = threadIdx.x;
+  {
+    const long long sidx = g * 32 + lane;
+    const long long i = REV ? (M - 1 - sidx) : sidx;
+    Elem e;
+    e.set_identity();
+    if (sidx < M) soa_load(items, seq, M, i, e);
+    Elem incl = warp_scan_inclusive<Elem, false>(e, lane);
+    Elem excl = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
+    if (sidx < M) soa_store(items, seq, M, i, excl);
+    if (lane == 31) soa_store(groups, seq, G, g, incl);
+  }
+  __threadfence();
+  unsigned int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(counter + seq, 1u);
+  ticket = __shfl_sync(kFull, ticket, 0);
+  if (ticket != (unsigned int)(G - 1)) return;
+  __threadfence();
+  const long long q = (G + 31) / 32;
+  const long long s0 = (long long)lane * q;
+  const long long s1 = (s0 + q < G) ? s0 + q : G;
   Elem acc;
   acc.set_identity();
 #pragma unroll 1
-  for (long long s = s0; s < s1; ++s) {
+  for (long long sidx = s0; sidx < s1; ++sidx) {
     Elem x;
-    soa_load(items, seq, M, REV ? (M - 1 - s) : s, x);
-    acc = ScanOp<Elem>::combine(acc, x);
+    soa_load_cg(groups, seq, G, sidx, x);
+    acc = (sidx == s0) ? x : ScanOp<Elem>::combine(acc, x);
   }
   Elem incl = warp_scan_inclusive<Elem, false>(acc, lane);
-  if (lane == 31) {
+  Elem run = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
+  if (lane == 31 && total_out) {
 #pragma unroll
-    for (int f = 0; f < Elem::NF; ++f) smem[warp * Elem::NF + f] = incl.v[f];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    Elem w;
-    w.set_identity();
-    if (lane < kMidBlock / 32) {
-#pragma unroll
-      for (int f = 0; f < Elem::NF; ++f) w.v[f] = smem[lane * Elem::NF + f];
-    }
-    Elem wi = warp_scan_inclusive<Elem, false>(w, lane);
-    Elem we = warp_exclusive_from_inclusive<Elem, false>(wi, lane);
-    if (lane == 31 && total_out) {
-#pragma unroll
-      for (int f = 0; f < Elem::NF; ++f) total_out[seq * Elem::NF + f] = wi.v[f];
-    }
-#pragma unroll
-    for (int f = 0; f < Elem::NF; ++f) smem[lane * Elem::NF + f] = we.v[f];
-  }
-  __syncthreads();
-  Elem run;
-  {
-    Elem wexcl;
-#pragma unroll
-    for (int f = 0; f < Elem::NF; ++f) wexcl.v[f] = smem[warp * Elem::NF + f];
-    Elem lexcl = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
-    run = ScanOp<Elem>::combine(wexcl, lexcl);
+    for (int f = 0; f < Elem::NF; ++f) total_out[seq * Elem::NF + f] = incl.v[f];
   }
 #pragma unroll 1
-  for (long long s = s0; s < s1; ++s) {
-    const long long i = REV ? (M - 1 - s) : s;
+  for (long long sidx = s0; sidx < s1; ++sidx) {
     Elem x;
-    soa_load(items, seq, M, i, x);
-    soa_store(items, seq, M, i, run);
-    if (s + 1 < s1) run = ScanOp<Elem>::combine(run, x);
+    soa_load_cg(groups, seq, G, sidx, x);
+    soa_store(groups, seq, G, sidx, run);
+    if (sidx + 1 < s1) run = ScanOp<Elem>::combine(run, x);
   }
-  if (ell_part) {  // fixed-order block sum of the per-warp log-likelihood partials
-    double* sred = smem + 32 * Elem::NF;
-    double s = 0.0;
-    for (long long i = tid; i < M; i += kMidBlock) s += ell_part[seq * M + i];
+  if (ell_part) {
+    double sum = 0.0;
+    for (long long i = lane; i < M; i += 32) sum += ell_part[seq * M + i];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(kFull, s, d);
-    __syncthreads();
-    if (lane == 0) sred[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double t = (lane < kMidBlock / 32) ? sred[lane] : 0.0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(kFull, t, d);
-      if (lane == 0) ell_out[seq] = t;
-    }
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(kFull, sum, d);
+    if (lane == 0) ell_out[seq] = sum;
   }
+  if (lane == 0) counter[seq] = 0u;
 }
 
 // =========================================================================================
 // K3
 // =========================================================================================
 template <int N, int NY, bool SMOOTH>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
 k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // [B][N], [B][N][N] lower
                const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
+               const double* __restrict__ group_pref,
                double* __restrict__ fm, double* __restrict__ fL,  // [B][T+1][N], [B][T+1][N][N]; index k+1 written
-               double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part) {
+               double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
+               unsigned int* __restrict__ counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -252,10 +260,13 @@ k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
 
+  if (SMOOTH && c == 0) counter[seq] = 0u;
   Gauss<N> x;
   load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
   {
     FElem<N> e;
+    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
+    filtering_apply<N>(x, e);
     soa_load(warp_pref, seq, Mw, c / 32, e);
     filtering_apply<N>(x, e);
     soa_load(chunk_pref, seq, Ppad, c, e);
@@ -295,10 +306,12 @@ k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
 template <int N>
 __global__ void __launch_bounds__(kBlock)
 k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __restrict__ fm,
-                const double* __restrict__ fL, double* __restrict__ chunk_suf, double* __restrict__ warp_stot) {
+                const double* __restrict__ fL, double* __restrict__ chunk_suf, double* __restrict__ warp_stot,
+                unsigned int* __restrict__ counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (c == 0) counter[seq] = 0u;
   const long long Mw = Ppad / 32;
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
@@ -325,11 +338,12 @@ k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __r
 // K5
 // =========================================================================================
 template <int N>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
 k_smooth_apply(SSMArgs a, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // smoothed state at index T
                long long carry_mstride, long long carry_Lstride,
                const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
+               const double* __restrict__ group_suf,
                const double* __restrict__ fm, const double* __restrict__ fL,
                double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
   const long long seq = blockIdx.y;
@@ -345,6 +359,8 @@ k_smooth_apply(SSMArgs a, long long T, int K, long long Ppad,
   if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
   {
     SElem<N> e;
+    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);  // groups are in scan (reverse) order
+    smoothing_apply<N>(xs, e);
     soa_load(warp_suf, seq, Mw, c / 32, e);
     smoothing_apply<N>(xs, e);
     soa_load(chunk_suf, seq, Ppad, c, e);
@@ -517,10 +533,12 @@ __device__ __forceinline__ void load_selem_dense(const double* g, const double* 
 template <int N>
 __global__ void __launch_bounds__(kBlock)
 k_escan_filter_reduce(const double* A, const double* b, const double* U, const double* eta, const double* Z,
-                      long long T, int K, long long Ppad, double* chunk_pref, double* warp_tot) {
+                      long long T, int K, long long Ppad, double* chunk_pref, double* warp_tot,
+                      unsigned int* counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (c == 0) counter[seq] = 0u;
   const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
   FElem<N> acc;
   acc.set_identity();
@@ -541,7 +559,8 @@ template <int N>
 __global__ void __launch_bounds__(kBlock)
 k_escan_filter_apply(const double* A, const double* b, const double* U, const double* eta, const double* Z,
                      long long T, int K, long long Ppad, const double* carry_m, const double* carry_L,
-                     const double* chunk_pref, const double* warp_pref, double* om, double* oL) {
+                     const double* chunk_pref, const double* warp_pref, const double* group_pref, double* om,
+                     double* oL) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
@@ -558,6 +577,8 @@ k_escan_filter_apply(const double* A, const double* b, const double* U, const do
     }
   }
   FElem<N> e;
+  soa_load(group_pref, seq, (Ppad / 32 + 31) / 32, c / 1024, e);
+  filtering_apply<N>(x, e);
   soa_load(warp_pref, seq, Ppad / 32, c / 32, e);
   filtering_apply<N>(x, e);
   soa_load(chunk_pref, seq, Ppad, c, e);
@@ -573,10 +594,11 @@ k_escan_filter_apply(const double* A, const double* b, const double* U, const do
 template <int N>
 __global__ void __launch_bounds__(kBlock)
 k_escan_smooth_reduce(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
-                      double* chunk_suf, double* warp_stot) {
+                      double* chunk_suf, double* warp_stot, unsigned int* counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  if (c == 0) counter[seq] = 0u;
   const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
   SElem<N> acc;
   acc.set_identity();
@@ -598,7 +620,7 @@ template <int N>
 __global__ void __launch_bounds__(kBlock)
 k_escan_smooth_apply(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
                      const double* carry_m, const double* carry_L, const double* chunk_suf, const double* warp_suf,
-                     double* om, double* oL) {
+                     const double* group_suf, double* om, double* oL) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const long long k0 = c * K, k1 = (k0 + K < T) ? k0 + K : T;
@@ -615,6 +637,8 @@ k_escan_smooth_apply(const double* g, const double* E, const double* D, long lon
     }
   }
   SElem<N> e;
+  soa_load(group_suf, seq, (Ppad / 32 + 31) / 32, (Ppad / 32 - 1 - c / 32) / 32, e);
+  smoothing_apply<N>(x, e);
   soa_load(warp_suf, seq, Ppad / 32, c / 32, e);
   smoothing_apply<N>(x, e);
   soa_load(chunk_suf, seq, Ppad, c, e);

@@ -10,11 +10,11 @@ struct SSMArgs;
 
 struct LaunchNY {
   void (*filter_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, double* chunk_pref,
-                        double* warp_tot, cudaStream_t);
+                        double* warp_tot, unsigned int* counter, cudaStream_t);
   void (*filter_apply)(int smooth, const SSMArgs&, long long T, int K, long long Ppad, long long B,
                        const double* carry_m, const double* carry_L, const double* chunk_pref,
-                       const double* warp_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
-                       double* ell_part, cudaStream_t);
+                       const double* warp_pref, const double* group_pref, double* fm, double* fL, double* chunk_suf,
+                       double* warp_stot, double* ell_part, unsigned int* counter_s, cudaStream_t);
   void (*filter_elements)(const SSMArgs&, long long T, long long B, const double* m0, const double* L0, double* A,
                           double* b, double* U, double* eta, double* Z, cudaStream_t);
   void (*loglik_terms)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* terms,
@@ -25,15 +25,16 @@ struct LaunchN {
   int n;
   int nf_filter, nf_smoother;
   const LaunchNY* (*for_ny)(int ny);
-  void (*mid_filter)(double* items, long long M, long long B, double* total, cudaStream_t);
-  void (*mid_smooth)(double* items, long long M, long long B, double* total, const double* ell_part,
-                     double* ell_out, cudaStream_t);
+  void (*mid_filter)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                     cudaStream_t);
+  void (*mid_smooth)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                     const double* ell_part, double* ell_out, cudaStream_t);
   void (*smooth_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* fm,
-                        const double* fL, double* chunk_suf, double* warp_stot, cudaStream_t);
+                        const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t);
   void (*smooth_apply)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* carry_m,
                        const double* carry_L, long long cms, long long cLs, const double* chunk_suf,
-                       const double* warp_suf, const double* fm, const double* fL, double* sm, double* sL,
-                       int write_terminal, cudaStream_t);
+                       const double* warp_suf, const double* group_suf, const double* fm, const double* fL,
+                       double* sm, double* sL, int write_terminal, cudaStream_t);
   void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                        double* cL, cudaStream_t);
   void (*carry_smoother)(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
@@ -42,15 +43,15 @@ struct LaunchN {
                             double* E, double* D, cudaStream_t);
   void (*escan_filter_reduce)(const double* A, const double* b, const double* U, const double* eta, const double* Z,
                               long long T, int K, long long Ppad, long long B, double* chunk_pref, double* warp_tot,
-                              cudaStream_t);
+                              unsigned int* counter, cudaStream_t);
   void (*escan_filter_apply)(const double* A, const double* b, const double* U, const double* eta, const double* Z,
                              long long T, int K, long long Ppad, long long B, const double* chunk_pref,
-                             const double* warp_pref, double* om, double* oL, cudaStream_t);
+                             const double* warp_pref, const double* group_pref, double* om, double* oL, cudaStream_t);
   void (*escan_smooth_reduce)(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
-                              long long B, double* chunk_suf, double* warp_stot, cudaStream_t);
+                              long long B, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t);
   void (*escan_smooth_apply)(const double* g, const double* E, const double* D, long long T, int K, long long Ppad,
-                             long long B, const double* chunk_suf, const double* warp_suf, double* om, double* oL,
-                             cudaStream_t);
+                             long long B, const double* chunk_suf, const double* warp_suf, const double* group_suf,
+                             double* om, double* oL, cudaStream_t);
   void (*filter_combine)(const double* A1, const double* b1, const double* U1, const double* e1, const double* Z1,
                          const double* A2, const double* b2, const double* U2, const double* e2, const double* Z2,
                          long long n, double* A, double* b, double* U, double* eta, double* Z, cudaStream_t);

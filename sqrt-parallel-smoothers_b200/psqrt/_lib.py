@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libpsqrt.so")
+_LIB_PATH = os.environ.get("PSQRT_LIB", os.path.join(_HERE, "libpsqrt.so"))  # PSQRT_LIB: tuning builds only
 _lib = None
 
 c_double_p = ctypes.c_void_p  # raw device addresses
@@ -86,9 +86,11 @@ def _stream():
 
 
 _ws_cache = {}
+WS_SLOT = 0   # staged calls of one pass must share a workspace; tests emulating several ranks on one GPU switch slots
 
 
-def workspace(nbytes: int, device: torch.device, slot: int = 0) -> torch.Tensor:
+def workspace(nbytes: int, device: torch.device, slot: Optional[int] = None) -> torch.Tensor:
+    slot = WS_SLOT if slot is None else slot
     key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:

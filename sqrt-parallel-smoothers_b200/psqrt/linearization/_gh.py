@@ -31,7 +31,8 @@ def _gauss_hermite_weights(n_dim: int, order: int = 3):
                      (order ** 2 * (np.polyval(hc[order - 1], roots[i])) ** 2) for i in range(order)])
     j = np.arange(order ** n_dim)
     table = np.stack([(j // (order ** r)) % order for r in range(n_dim)], axis=0)
-    wm = np.prod(w_1d[table], axis=0) / (np.sqrt(np.pi) ** n_dim)
+    s = 1 / (np.sqrt(np.pi) ** n_dim)
+    wm = s * np.prod(w_1d[table], axis=0)
     xi = (np.sqrt(2) * roots[table]).T.copy()        # [P, n]
     return wm, wm, xi
 

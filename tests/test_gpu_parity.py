@@ -88,6 +88,45 @@ def test_pass_vs_sequential_oracle():
     assert abs(ell.item() - ells) <= TOL_ELL * abs(ells)
 
 
+@pytest.mark.parametrize("n,ny,R,T", [(4, 2, 3, 1000), (5, 2, 2, 301), (8, 4, 4, 260), (1, 1, 2, 64), (2, 3, 8, 50)])
+def test_staged_calls_fake_ranks(n, ny, R, T):
+    """The time-sharded path (psqrt/dist.py steps 1-5) with R fake ranks on one GPU: shard totals,
+    carry folding, carry application, suffix carries -- equal to the unsharded oracle."""
+    from psqrt import _lib
+    from psqrt import dist as pdist
+    case = lgssm_case(n, ny, T, seed=9 * n + ny)
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    ssm = _ssm(case)
+    ys = _g(case["ys"])
+    m0, L0 = _g(case["m0"])[None], _g(case["L0"])[None]
+    spans = [pdist.shard_bounds(T, R, r) for r in range(R)]
+    try:
+        totals = []
+        for r, (t0, t1) in enumerate(spans):
+            _lib.WS_SLOT = 100 + r
+            totals.append(_lib.filter_reduce(ssm, ys[t0:t1][None].contiguous(), n))
+        totals = torch.stack(totals)
+        outs, payloads, ell_sum = [], [], 0.0
+        for r, (t0, t1) in enumerate(spans):
+            _lib.WS_SLOT = 100 + r
+            cm, cL = _lib.carry_filter(totals, r, m0, L0)
+            fm, fL, ell, stot = _lib.filter_apply(ssm, ys[t0:t1][None].contiguous(), cm, cL, smooth=True, loglik=True)
+            ell_sum += ell.item()
+            outs.append((fm, fL))
+            payloads.append(stot)
+            _check_traj(f"filtered shard {r}", fm[0], fL[0], ofm[t0:t1 + 1], ofc[t0:t1 + 1])
+        assert abs(ell_sum - oell) <= TOL_ELL * abs(oell)
+        stotals = torch.stack(payloads)
+        mT, LT = outs[-1][0][:, -1].contiguous(), outs[-1][1][:, -1].contiguous()
+        for r, (t0, t1) in enumerate(spans):
+            _lib.WS_SLOT = 100 + r
+            scm, scL = _lib.carry_smoother(stotals, r, R, mT, LT)
+            sm, sL = _lib.smoother_apply(ssm, outs[r][0], outs[r][1], scm, scL, write_terminal=True)
+            _check_traj(f"smoothed shard {r}", sm[0], sL[0], osm[t0:t1 + 1], osc[t0:t1 + 1])
+    finally:
+        _lib.WS_SLOT = 0
+
+
 def test_batched_pass():
     """batch axis: independent sequences sharing the model (config 5 shape)."""
     from psqrt import _lib
