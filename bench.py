@@ -221,7 +221,8 @@ def run_psqrt(args):
     model = make_lgssm(NX, NY)
     ys_np = simulate(model, T, seed=1000 + rank)
     g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
-    ssm = LinearizedSSM(*[g(model[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")])
+    ssm = LinearizedSSM(*[g(model[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")],
+                        host=None if args.no_host_model else {k: model[k] for k in ("F", "cholQ", "b", "H", "cholR", "c")})
     ys = g(ys_np)
     m0, L0 = g(model["m0"]), g(model["L0"])
     x0 = psqrt.MVNSqrt(m0, L0)
@@ -367,7 +368,7 @@ def run_psqrt(args):
                        "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
                        "l2": "working set per pass (y 16 MB + filtered 160 MB + smoothed 160 MB) exceeds the 126 MB L2; "
                              "no explicit flush"},
-            "e2e": e2e, "gpu_launches": (6 if world == 1 else 9) * args.steps,
+            "e2e": e2e, "gpu_launches": (5 if world == 1 else 7) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
@@ -385,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="psqrt", choices=["psqrt", "reference"])
     ap.add_argument("--T", type=int, default=T_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-model", action="store_true", help="load the model from HBM per step instead of by value")
     ap.add_argument("--chunk", type=int, default=0, help="chunk length override (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -53,6 +53,10 @@ typedef struct psqrt_ssm {
   const double *F, *cholQ, *b, *H, *cholR, *c;
   int64_t F_ts, cholQ_ts, b_ts, H_ts, cholR_ts, c_ts;
   int64_t F_bs, cholQ_bs, b_bs, H_bs, cholR_bs, c_bs;
+  /* Optional HOST mirrors of the six arrays (NULL when unknown).  When the model is shared by all
+   * steps and sequences (every stride 0) and its host mirrors are given, the sweeps carry the
+   * model by value in their kernel parameters, i.e. as constant-bank operands. */
+  const double *hF, *hcholQ, *hb, *hH, *hcholR, *hc;
 } psqrt_ssm;
 
 typedef struct psqrt_plan {
@@ -149,6 +153,30 @@ int psqrt_smoother_combine(const double* g1, const double* E1, const double* D1,
 int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t batch, void* stream);
 int psqrt_chol_update_batched(double* L, const double* V, int n, int k, double alpha, int64_t batch,
                               void* stream);
+
+/* ---- linearization of the built-in models as device code (one thread per time step) -----------
+ * Replaces vmap(linearization_method(model, nominal)) of parallel/_filtering.py:110-119 and
+ * _smoothing.py:50-55 for the models of the reference's tests / notebooks:
+ *   PSQRT_MODEL_CT_TRANSITION         tests/bearings/bearings_utils.py:7-46    params {dt}                 5 -> 5
+ *   PSQRT_MODEL_BEARINGS_OBSERVATION  tests/bearings/bearings_utils.py:49-69   params {s1x,s1y,s2x,s2y}    5 -> 2
+ *   PSQRT_MODEL_RICKER_TRANSITION     notebooks/population_model.py:23-62      params {sqrt(Q)}            1 -> 1 (conditional moments)
+ *   PSQRT_MODEL_POISSON_OBSERVATION   notebooks/population_model.py:84-129     params {lam}                1 -> 1 (conditional moments)
+ * lin_id PSQRT_LIN_EXTENDED (linearization/_extended.py:51-70; xi/wm/wc/nom_L unused, chol written only for
+ * conditional-moments models) or PSQRT_LIN_SLR (linearization/_sigma_points.py:25-100 with the unit sigma
+ * points xi [n_points, n] and weights wm, wc [n_points] -- cubature: _cubature.py:63-85, Gauss-Hermite:
+ * _gh.py:73-126 -- incl. the Cholesky downdates of _utils.py:13-19,39-81).
+ * model_params is a HOST array; nom_m [count, n], nom_L [count, n, n], m_q [d], chol_q [d, d] (functional models),
+ * outputs F [count, d, n], chol [count, d, d], b [count, d] are device arrays. */
+#define PSQRT_MODEL_CT_TRANSITION 1
+#define PSQRT_MODEL_BEARINGS_OBSERVATION 2
+#define PSQRT_MODEL_RICKER_TRANSITION 3
+#define PSQRT_MODEL_POISSON_OBSERVATION 4
+#define PSQRT_LIN_EXTENDED 0
+#define PSQRT_LIN_SLR 1
+int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id, const double* xi,
+                            const double* wm, const double* wc, int n_points, const double* nom_m,
+                            const double* nom_L, int64_t count, const double* m_q, const double* chol_q,
+                            double* F, double* chol, double* b, void* stream);
 
 #ifdef __cplusplus
 }

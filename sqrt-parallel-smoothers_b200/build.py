@@ -47,6 +47,8 @@ def _nvcc() -> str:
 def _digest(extra: str) -> str:
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)):
+        if not os.path.isfile(os.path.join(CSRC, name)):
+            continue
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())

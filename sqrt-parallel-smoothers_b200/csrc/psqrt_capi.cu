@@ -16,6 +16,7 @@ void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, 
 
 namespace {
 
+using psq::HostModel;
 using psq::LaunchN;
 using psq::LaunchNY;
 using psq::SSMArgs;
@@ -65,6 +66,7 @@ int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_
 // element scans, so a workspace sized for the op can be reused across stages.
 struct Ws {
   double *chunk_pref, *warp_tot, *group_f, *ftotal, *chunk_suf, *warp_stot, *group_s, *stotal, *ell_part, *ell_tmp;
+  double* selems;  // [B][K][nf_smoother][Ppad] smoothing elements handed from the forward to the backward sweep
   unsigned int *counter_f, *counter_s;
   size_t doubles;
 };
@@ -90,6 +92,7 @@ Ws carve(void* base, const psqrt_plan& p, int64_t B) {
   w.ell_tmp = take((size_t)B);
   w.counter_f = (unsigned int*)take((size_t)B);   // one 8-byte slot per sequence, used as uint32
   w.counter_s = (unsigned int*)take((size_t)B);
+  w.selems = take((size_t)B * (size_t)p.chunk_len * (size_t)p.nf_smoother * (size_t)p.n_chunks_pad);
   w.doubles = off;
   return w;
 }
@@ -102,6 +105,19 @@ SSMArgs make_args(const psqrt_ssm* s, const double* y, int ny, int64_t T) {
   a.sF = s->F_bs; a.sQ = s->cholQ_bs; a.sb = s->b_bs; a.sH = s->H_bs; a.sR = s->cholR_bs; a.sc = s->c_bs;
   a.sy = (long long)T * ny;
   return a;
+}
+
+// Host mirrors usable?  Only for a model shared by every step and sequence.
+const HostModel* host_model(const psqrt_ssm* s, bool need_obs, HostModel* out) {
+  if (!s->hF || !s->hcholQ || !s->hb) return nullptr;
+  if (s->F_ts || s->cholQ_ts || s->b_ts || s->F_bs || s->cholQ_bs || s->b_bs) return nullptr;
+  if (need_obs) {
+    if (!s->hH || !s->hcholR || !s->hc) return nullptr;
+    if (s->H_ts || s->cholR_ts || s->c_ts || s->H_bs || s->cholR_bs || s->c_bs) return nullptr;
+  }
+  out->F = s->hF; out->Q = s->hcholQ; out->bq = s->hb;
+  out->H = need_obs ? s->hH : nullptr; out->R = need_obs ? s->hcholR : nullptr; out->c = need_obs ? s->hc : nullptr;
+  return out;
 }
 
 int check_launch() { return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA; }
@@ -184,7 +200,8 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
-  c.lny->filter_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot,
+  HostModel hmv;
+  c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot,
                        c.ws.counter_f, st);
   c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, ftotal ? ftotal : c.ws.ftotal,
                    st);
@@ -210,9 +227,10 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
   const int smooth = stotal != nullptr;
-  c.lny->filter_apply(smooth, a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, c.ws.chunk_pref,
+  HostModel hmv;
+  c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, c.ws.chunk_pref,
                       c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
-                      ell ? c.ws.ell_part : nullptr, c.ws.counter_s, st);
+                      ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.selems, st);
   if (smooth) {
     c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, stotal,
                      ell ? c.ws.ell_part : nullptr, ell, st);
@@ -236,13 +254,13 @@ int psqrt_carry_smoother(const double* totals, int rank, int n_ranks, int64_t ba
 int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
                          double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
-  if (!ssm_ok(ssm, false) || !fm || !fL || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
+  (void)ssm; (void)fm; (void)fL;  // the smoothing elements were stored in the workspace by psqrt_filter_apply
+  if (!carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
-  SSMArgs a = make_args(ssm, nullptr, 0, T);
-  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, nx, (long long)nx * nx,
-                     c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, write_terminal,
+  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, nx, (long long)nx * nx,
+                     c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.selems, sm, sL, write_terminal,
                      (cudaStream_t)stream);
   return check_launch();
 }
@@ -261,10 +279,9 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
                           ws_bytes, stream);
   if (rc || !smooth) return rc;
   // terminal carry = filtered state at index T of every sequence
-  SSMArgs a = make_args(ssm, nullptr, 0, T);
-  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
-                     fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
-                     c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, 1, (cudaStream_t)stream);
+  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx, fL + (size_t)T * nx * nx,
+                     (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot,
+                     c.ws.group_s, c.ws.selems, sm, sL, 1, (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -276,13 +293,14 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
-  c.ln->smooth_reduce(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
-                      c.ws.counter_s, st);
+  HostModel hmv;
+  c.ln->smooth_reduce(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
+                      c.ws.counter_s, c.ws.selems, st);
   c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
                    st);
-  c.ln->smooth_apply(a, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx,
-                     fL + (size_t)T * nx * nx, (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf,
-                     c.ws.warp_stot, c.ws.group_s, fm, fL, sm, sL, 1, st);
+  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx, fL + (size_t)T * nx * nx,
+                     (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot,
+                     c.ws.group_s, c.ws.selems, sm, sL, 1, st);
   return check_launch();
 }
 

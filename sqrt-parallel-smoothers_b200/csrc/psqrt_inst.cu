@@ -2,6 +2,8 @@
 // -DPSQ_N=<nx>); observation dimensions 1..PSQ_MAX_NY are instantiated for that nx.
 #include "psqrt_launch.h"
 
+#include <stdint.h>
+
 #ifndef PSQ_N
 #error "compile with -DPSQ_N=<nx>"
 #endif
@@ -25,25 +27,70 @@ namespace {
 
 constexpr int N = PSQ_N;
 
+// Fill a by-value model (kernel parameter) from the host mirrors.
+template <int NY>
+SrcVal<N, NY> make_src_val(const HostModel& h, const SSMArgs& a) {
+  SrcVal<N, NY> s;
+  for (int i = 0; i < N * N; ++i) { s.m.F[i] = h.F[i]; s.m.Q[i] = h.Q[i]; }
+  for (int i = 0; i < N; ++i) s.m.bq[i] = h.bq[i];
+  for (int i = 0; i < NY * N; ++i) s.m.H[i] = h.H ? h.H[i] : 0.0;
+  for (int i = 0; i < NY * NY; ++i) s.m.R[i] = h.R ? h.R[i] : 0.0;
+  for (int i = 0; i < NY; ++i) s.m.c[i] = h.c ? h.c[i] : 0.0;
+  s.y = a.y; s.ty = a.ty; s.sy = a.sy;
+  return s;
+}
+
 inline dim3 sweep_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kBlock), (unsigned)B, 1); }
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 template <int NY>
 struct NYImpl {
-  static void filter_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, double* chunk_pref,
-                            double* warp_tot, unsigned int* counter, cudaStream_t st) {
-    k_filter_reduce<N, NY><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, chunk_pref, warp_tot, counter);
+  static void filter_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
+                            double* chunk_pref, double* warp_tot, unsigned int* counter, cudaStream_t st) {
+    if (hm) {
+      k_filter_reduce<N, NY, SrcVal<N, NY>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<NY>(*hm, a), T, K, Ppad,
+                                                                                   chunk_pref, warp_tot, counter);
+    } else {
+      k_filter_reduce<N, NY, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, chunk_pref, warp_tot,
+                                                                            counter);
+    }
   }
-  static void filter_apply(int smooth, const SSMArgs& a, long long T, int K, long long Ppad, long long B,
-                           const double* cm, const double* cL, const double* chunk_pref, const double* warp_pref,
-                           const double* group_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
-                           double* ell_part, unsigned int* counter_s, cudaStream_t st) {
-    if (smooth)
-      k_filter_apply<N, NY, true><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
-          a, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s);
-    else
-      k_filter_apply<N, NY, false><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
-          a, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s);
+  static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+  template <bool SMOOTH, class SRC>
+  static void filter_apply_t(const SRC& src, long long T, int K, long long Ppad, long long B, const double* cm,
+                             const double* cL, const double* chunk_pref, const double* warp_pref,
+                             const double* group_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
+                             double* ell_part, unsigned int* counter_s, double* selems, cudaStream_t st) {
+    if constexpr (tma::Cfg<N>::S > 0) {
+      if (aligned16(fm) && aligned16(fL)) {   // staged stores (TMA bulk copies)
+        const size_t smem = tma::Cfg<N>::smem_bytes(kBlock);
+        auto kern = k_filter_apply_tma<N, NY, SMOOTH, SRC>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm,
+                                                       fL, chunk_suf, warp_stot, ell_part, counter_s, selems);
+        return;
+      }
+    }
+    k_filter_apply<N, NY, SMOOTH, SRC><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
+        src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s,
+        selems);
+  }
+  static void filter_apply(int smooth, const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad,
+                           long long B, const double* cm, const double* cL, const double* chunk_pref,
+                           const double* warp_pref, const double* group_pref, double* fm, double* fL,
+                           double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
+                           double* selems, cudaStream_t st) {
+#define PSQ_FA(SM, SRCV)                                                                                             \
+  filter_apply_t<SM>(SRCV, T, K, Ppad, B, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot,  \
+                     ell_part, counter_s, selems, st)
+    if (hm) {
+      const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
+      if (smooth) PSQ_FA(true, sv); else PSQ_FA(false, sv);
+    } else {
+      const SrcPtr sp{a};
+      if (smooth) PSQ_FA(true, sp); else PSQ_FA(false, sp);
+    }
+#undef PSQ_FA
   }
   static void filter_elements(const SSMArgs& a, long long T, long long B, const double* m0, const double* L0,
                               double* A, double* b, double* U, double* eta, double* Z, cudaStream_t st) {
@@ -87,16 +134,39 @@ void mid_smooth(double* items, long long M, long long B, double* groups, unsigne
   k_mid_scan<SElem<N>, true><<<mid_grid(M, B), 32, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, ell_part,
                                                           ell_out);
 }
-void smooth_reduce(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* fm,
-                   const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t st) {
-  k_smooth_reduce<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, fm, fL, chunk_suf, warp_stot, counter);
+void smooth_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
+                   const double* fm, const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter,
+                   double* selems, cudaStream_t st) {
+  if (hm)
+    k_smooth_reduce<N, SrcVal<N, 1>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<1>(*hm, a), T, K, Ppad, fm, fL,
+                                                                            chunk_suf, warp_stot, counter, selems);
+  else
+    k_smooth_reduce<N, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, fm, fL, chunk_suf,
+                                                                      warp_stot, counter, selems);
 }
-void smooth_apply(const SSMArgs& a, long long T, int K, long long Ppad, long long B, const double* cm,
-                  const double* cL, long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
-                  const double* group_suf, const double* fm, const double* fL, double* sm, double* sL,
-                  int write_terminal, cudaStream_t st) {
-  k_smooth_apply<N><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(a, T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf,
-                                                           group_suf, fm, fL, sm, sL, write_terminal);
+template <int NN>
+void smooth_apply_t(long long T, int K, long long Ppad, long long B, const double* cm, const double* cL,
+                    long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
+                    const double* group_suf, const double* selems, double* sm, double* sL, int write_terminal,
+                    cudaStream_t st) {
+  if constexpr (tma::Cfg<NN>::S > 0) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if (al(sm) && al(sL)) {   // staged loads + stores (TMA bulk copies)
+      const size_t smem = tma::Cfg<NN>::smem_bytes(kBlock);
+      auto kern = k_smooth_apply_tma<NN>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
+                                                     selems, sm, sL, write_terminal);
+      return;
+    }
+  }
+  k_smooth_apply<NN><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
+                                                            selems, sm, sL, write_terminal);
+}
+void smooth_apply(long long T, int K, long long Ppad, long long B, const double* cm, const double* cL, long long cms,
+                  long long cLs, const double* chunk_suf, const double* warp_suf, const double* group_suf,
+                  const double* selems, double* sm, double* sL, int write_terminal, cudaStream_t st) {
+  smooth_apply_t<N>(T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, selems, sm, sL, write_terminal, st);
 }
 void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                   double* cL, cudaStream_t st) {

@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "psqrt_math.cuh"
+#include "psqrt_tma.cuh"
 
 namespace psq {
 
@@ -57,6 +58,23 @@ __device__ __forceinline__ StepPtrs step_ptrs(const SSMArgs& a, long long seq, l
   p.y = a.y ? a.y + seq * a.sy + k * a.ty : nullptr;
   return p;
 }
+
+// Where a sweep gets the model of step k from: pointers + strides (any model), or the model
+// itself carried by value in the kernel parameters (time-invariant models whose entries the
+// host knows: they become constant-bank operands, see psq::ModelVals).
+struct SrcPtr {
+  SSMArgs a;
+  __device__ __forceinline__ StepPtrs at(long long seq, long long k) const { return step_ptrs(a, seq, k); }
+};
+template <int N, int NY>
+struct SrcVal {
+  ModelVals<N, NY> m;
+  const double* y;
+  long long ty, sy;
+  __device__ __forceinline__ StepVals<N, NY> at(long long seq, long long k) const {
+    return StepVals<N, NY>{m, y ? y + seq * sy + k * ty : nullptr};
+  }
+};
 
 // ---- element traits: combine(acc, x) with acc = everything earlier in SCAN order ------------
 template <class Elem>
@@ -139,12 +157,32 @@ __device__ __forceinline__ void store_gauss_dense(double* m, double* L, const Ga
   }
 }
 
+// Smoothing elements travel from the forward sweep (K3) to the backward sweep (K5) through a scratch
+// array, so K5 only applies them instead of re-deriving each one from the filtered state with another
+// 2N x 2N triangularisation.  Layout [B][K][NF][Ppad]: step j of chunk c keeps field f at
+// ((j * NF + f) * Ppad + c), i.e. the 32 lanes of a warp (consecutive chunks, same j) touch 32
+// consecutive doubles -- fully coalesced plain loads / stores, no staging needed.
+template <int N>
+__device__ __forceinline__ void selem_store(double* selems, long long seq, int K, long long Ppad, long long c, int j,
+                                            const SElem<N>& e) {
+  double* p = selems + ((seq * K + j) * SElem<N>::NF) * Ppad + c;
+#pragma unroll
+  for (int f = 0; f < SElem<N>::NF; ++f) p[f * Ppad] = e.v[f];
+}
+template <int N>
+__device__ __forceinline__ void selem_load(const double* selems, long long seq, int K, long long Ppad, long long c,
+                                           int j, SElem<N>& e) {
+  const double* p = selems + ((seq * K + j) * SElem<N>::NF) * Ppad + c;
+#pragma unroll
+  for (int f = 0; f < SElem<N>::NF; ++f) e.v[f] = __ldg(p + f * Ppad);
+}
+
 // =========================================================================================
 // K1
 // =========================================================================================
-template <int N, int NY>
+template <int N, int NY, class SRC>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K1)
-k_filter_reduce(SSMArgs a, long long T, int K, long long Ppad, double* __restrict__ chunk_pref,
+k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, double* __restrict__ chunk_pref,
                 double* __restrict__ warp_tot, unsigned int* __restrict__ counter) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -156,7 +194,7 @@ k_filter_reduce(SSMArgs a, long long T, int K, long long Ppad, double* __restric
   const long long k1 = (k0 + K < T) ? k0 + K : T;
 #pragma unroll 1
   for (long long k = k0; k < k1; ++k) {
-    StepPtrs p = step_ptrs(a, seq, k);
+    const auto p = src.at(seq, k);
     filter_reduce_step<N, NY>(acc, p);
   }
   FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(acc, lane);
@@ -244,15 +282,15 @@ k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ groups,
 // =========================================================================================
 // K3
 // =========================================================================================
-template <int N, int NY, bool SMOOTH>
+template <int N, int NY, bool SMOOTH, class SRC>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
-k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
+k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // [B][N], [B][N][N] lower
                const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
                const double* __restrict__ group_pref,
                double* __restrict__ fm, double* __restrict__ fL,  // [B][T+1][N], [B][T+1][N][N]; index k+1 written
                double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
-               unsigned int* __restrict__ counter) {
+               unsigned int* __restrict__ counter, double* __restrict__ selems) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -280,11 +318,12 @@ k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
   sacc.set_identity();
 #pragma unroll 1
   for (long long k = k0; k < k1; ++k) {
-    StepPtrs p = step_ptrs(a, seq, k);
+    const auto p = src.at(seq, k);
     SElem<N> se;
     ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
     store_gauss_dense<N>(fmS + (k + 1) * N, fLS + (k + 1) * N * N, x);
     if (SMOOTH) {
+      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
       if (k == k0) sacc = se;
       else sacc = smoothing_combine<N>(se, sacc);  // se is the later side
     }
@@ -303,11 +342,11 @@ k_filter_apply(SSMArgs a, long long T, int K, long long Ppad,
 }
 
 // Standalone smoothing reduce (smoothing(...) called on an existing filter trajectory).
-template <int N>
+template <int N, class SRC>
 __global__ void __launch_bounds__(kBlock)
-k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __restrict__ fm,
+k_smooth_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, const double* __restrict__ fm,
                 const double* __restrict__ fL, double* __restrict__ chunk_suf, double* __restrict__ warp_stot,
-                unsigned int* __restrict__ counter) {
+                unsigned int* __restrict__ counter, double* __restrict__ selems) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -321,11 +360,12 @@ k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __r
   sacc.set_identity();
 #pragma unroll 1
   for (long long k = k0; k < k1; ++k) {
-    StepPtrs p = step_ptrs(a, seq, k);
+    const auto p = src.at(seq, k);
     Gauss<N> xf;
     load_gauss_dense<N>(fmS + k * N, fLS + k * N * N, xf);
     SElem<N> se;
-    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+    smoothing_element<N>(xf, p, se);
+    selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
     sacc = (k == k0) ? se : smoothing_combine<N>(se, sacc);
   }
   SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
@@ -339,12 +379,11 @@ k_smooth_reduce(SSMArgs a, long long T, int K, long long Ppad, const double* __r
 // =========================================================================================
 template <int N>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
-k_smooth_apply(SSMArgs a, long long T, int K, long long Ppad,
+k_smooth_apply(long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // smoothed state at index T
                long long carry_mstride, long long carry_Lstride,
                const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
-               const double* __restrict__ group_suf,
-               const double* __restrict__ fm, const double* __restrict__ fL,
+               const double* __restrict__ group_suf, const double* __restrict__ selems,
                double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -366,18 +405,199 @@ k_smooth_apply(SSMArgs a, long long T, int K, long long Ppad,
     soa_load(chunk_suf, seq, Ppad, c, e);
     smoothing_apply<N>(xs, e);
   }
-  const double* fmS = fm + seq * (T + 1) * N;
-  const double* fLS = fL + seq * (T + 1) * N * N;
+  SElem<N> se;
+  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
 #pragma unroll 1
   for (long long k = k1 - 1; k >= k0; --k) {
-    StepPtrs p = step_ptrs(a, seq, k);
-    Gauss<N> xf;
-    load_gauss_dense<N>(fmS + k * N, fLS + k * N * N, xf);
-    SElem<N> se;
-    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+    SElem<N> nxt;
+    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);  // in flight during the apply
     smoothing_apply<N>(xs, se);
     store_gauss_dense<N>(smS + k * N, sLS + k * N * N, xs);
+    se = nxt;
   }
+}
+
+// =========================================================================================
+// Staged variants of K5 and K3 (even N, 16-byte aligned trajectories): records move between HBM
+// and a per-lane shared-memory slice with TMA bulk copies (psqrt_tma.cuh).
+// =========================================================================================
+template <int N>
+__device__ __forceinline__ void load_gauss_smem(const double* m, const double* L, Gauss<N>& x) {
+  static_assert(N % 2 == 0, "staged path needs even N");
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(m + i);
+    x.m[i] = v.x;
+    x.m[i + 1] = v.y;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; j += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(L + i * N + j);
+      x.Lc(i, j) = v.x;
+      if (j + 1 <= i) x.Lc(i, j + 1) = v.y;
+    }
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_gauss_smem(double* m, double* L, const Gauss<N>& x) {
+#pragma unroll
+  for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(m + i) = make_double2(x.m[i], x.m[i + 1]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      const double a = (j <= i) ? x.Lc(i, j) : 0.0;
+      const double b = (j + 1 <= i) ? x.Lc(i, j + 1) : 0.0;
+      *reinterpret_cast<double2*>(L + i * N + j) = make_double2(a, b);
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
+k_smooth_apply_tma(long long T, int K, long long Ppad,
+                   const double* __restrict__ carry_m, const double* __restrict__ carry_L,
+                   long long carry_mstride, long long carry_Lstride,
+                   const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
+                   const double* __restrict__ group_suf, const double* __restrict__ selems,
+                   double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
+  using CF = tma::Cfg<N>;
+  constexpr int S = CF::SS, NBUF = CF::NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* slice = reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * CF::LANE;
+
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  if (k0 >= k1) return;
+  double* smS = sm + seq * (T + 1) * N;
+  double* sLS = sL + seq * (T + 1) * N * N;
+  SElem<N> se;
+  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
+
+  Gauss<N> xs;
+  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
+  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
+  {
+    SElem<N> e;
+    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);
+    smoothing_apply<N>(xs, e);
+    soa_load(warp_suf, seq, Mw, c / 32, e);
+    smoothing_apply<N>(xs, e);
+    soa_load(chunk_suf, seq, Ppad, c, e);
+    smoothing_apply<N>(xs, e);
+  }
+  // output tiles [lo, hi) of up to S records, walked from the top slot down, NBUF tiles in rotation
+  int t = 0;
+  long long hi = k1;
+#pragma unroll 1
+  for (long long k = k1 - 1; k >= k0; --k) {
+    SElem<N> nxt;
+    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);  // in flight during the apply
+    smoothing_apply<N>(xs, se);
+    const long long lo = (hi - S > k0) ? hi - S : k0;
+    double* buf = slice + (t % NBUF) * CF::BUF_DOUBLES;
+    if (k == hi - 1) {  // first write into this buffer: the store issued NBUF tiles ago must have drained it
+      if (NBUF > 1) tma::bulk_wait_read<NBUF - 1>(); else tma::bulk_wait_read<0>();
+    }
+    const int slot = (int)(k - lo);
+    store_gauss_smem<N>(buf + slot * N, buf + S * N + slot * N * N, xs);
+    if (k == lo) {
+      const unsigned cnt = (unsigned)(hi - lo);
+      tma::fence_proxy_async();
+      tma::bulk_store(smS + lo * N, buf, cnt * N * (unsigned)sizeof(double));
+      tma::bulk_store(sLS + lo * N * N, buf + S * N, cnt * N * N * (unsigned)sizeof(double));
+      tma::bulk_commit();
+      hi = lo;
+      ++t;
+    }
+    se = nxt;
+  }
+  tma::bulk_wait<0>();
+}
+
+template <int N, int NY, bool SMOOTH, class SRC>
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
+k_filter_apply_tma(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
+                   const double* __restrict__ carry_m, const double* __restrict__ carry_L,
+                   const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
+                   const double* __restrict__ group_pref,
+                   double* __restrict__ fm, double* __restrict__ fL,
+                   double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
+                   unsigned int* __restrict__ counter, double* __restrict__ selems) {
+  using CF = tma::Cfg<N>;
+  constexpr int S = CF::SS, NBUF = CF::NB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* slice = reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * CF::LANE;
+
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  if (SMOOTH && c == 0) counter[seq] = 0u;
+  Gauss<N> x;
+  load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
+  {
+    FElem<N> e;
+    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
+    filtering_apply<N>(x, e);
+    soa_load(warp_pref, seq, Mw, c / 32, e);
+    filtering_apply<N>(x, e);
+    soa_load(chunk_pref, seq, Ppad, c, e);
+    filtering_apply<N>(x, e);
+  }
+  double* fmS = fm + seq * (T + 1) * N;
+  double* fLS = fL + seq * (T + 1) * N * N;
+  if (c == 0) store_gauss_dense<N>(fmS, fLS, x);
+  double ell = 0.0;
+  SElem<N> sacc;
+  sacc.set_identity();
+  int t = 0;
+  long long lo = k0;  // first step of the current output tile
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    const auto p = src.at(seq, k);
+    SElem<N> se;
+    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
+    const int slot = (int)(k - lo);
+    double* buf = slice + (t % NBUF) * CF::BUF_DOUBLES;
+    if (slot == 0) {  // first write into this buffer: the store issued NBUF tiles ago must have drained it
+      if (NBUF > 1) tma::bulk_wait_read<NBUF - 1>(); else tma::bulk_wait_read<0>();
+    }
+    store_gauss_smem<N>(buf + slot * N, buf + S * N + slot * N * N, x);
+    if (slot == S - 1 || k == k1 - 1) {
+      const unsigned cnt = (unsigned)(slot + 1);
+      tma::fence_proxy_async();
+      tma::bulk_store(fmS + (lo + 1) * N, buf, cnt * N * (unsigned)sizeof(double));
+      tma::bulk_store(fLS + (lo + 1) * N * N, buf + S * N, cnt * N * N * (unsigned)sizeof(double));
+      tma::bulk_commit();
+      lo = k + 1;
+      ++t;
+    }
+    if (SMOOTH) {
+      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
+      if (k == k0) sacc = se;
+      else sacc = smoothing_combine<N>(se, sacc);
+    }
+  }
+  if (ell_part) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
+    if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
+  }
+  if (SMOOTH) {
+    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
+    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+    soa_store(chunk_suf, seq, Ppad, c, excl);
+    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+  }
+  tma::bulk_wait<0>();
 }
 
 // =========================================================================================
@@ -451,7 +671,7 @@ __global__ void k_smoother_elements(SSMArgs a, long long T, long long B, const d
   SElem<N> se;
   if (k < T) {
     StepPtrs p = step_ptrs(a, seq, k);
-    smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+    smoothing_element<N>(xf, p, se);
   } else {
 #pragma unroll
     for (int r = 0; r < N; ++r) {

@@ -8,13 +8,18 @@ namespace psq {
 
 struct SSMArgs;
 
+// host mirrors of a time- and batch-invariant model (all six non-null) or nullptr entries
+struct HostModel {
+  const double *F, *Q, *bq, *H, *R, *c;
+};
+
 struct LaunchNY {
-  void (*filter_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, double* chunk_pref,
+  void (*filter_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, double* chunk_pref,
                         double* warp_tot, unsigned int* counter, cudaStream_t);
-  void (*filter_apply)(int smooth, const SSMArgs&, long long T, int K, long long Ppad, long long B,
+  void (*filter_apply)(int smooth, const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                        const double* carry_m, const double* carry_L, const double* chunk_pref,
                        const double* warp_pref, const double* group_pref, double* fm, double* fL, double* chunk_suf,
-                       double* warp_stot, double* ell_part, unsigned int* counter_s, cudaStream_t);
+                       double* warp_stot, double* ell_part, unsigned int* counter_s, double* selems, cudaStream_t);
   void (*filter_elements)(const SSMArgs&, long long T, long long B, const double* m0, const double* L0, double* A,
                           double* b, double* U, double* eta, double* Z, cudaStream_t);
   void (*loglik_terms)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* terms,
@@ -29,11 +34,12 @@ struct LaunchN {
                      cudaStream_t);
   void (*mid_smooth)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                      const double* ell_part, double* ell_out, cudaStream_t);
-  void (*smooth_reduce)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* fm,
-                        const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, cudaStream_t);
-  void (*smooth_apply)(const SSMArgs&, long long T, int K, long long Ppad, long long B, const double* carry_m,
+  void (*smooth_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, const double* fm,
+                        const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, double* selems,
+                        cudaStream_t);
+  void (*smooth_apply)(long long T, int K, long long Ppad, long long B, const double* carry_m,
                        const double* carry_L, long long cms, long long cLs, const double* chunk_suf,
-                       const double* warp_suf, const double* group_suf, const double* fm, const double* fL,
+                       const double* warp_suf, const double* group_suf, const double* selems,
                        double* sm, double* sL, int write_terminal, cudaStream_t);
   void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                        double* cL, cudaStream_t);

@@ -30,6 +30,35 @@ namespace psq {
 
 constexpr double kHalfLog2Pi = 0.91893853320467274178;  // log(2*pi)/2
 
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, >= 20
+// good bits) + two Newton steps -> ~1 ulp, no slow-path call.  Inputs here are norms and diagonal
+// entries of factors; 0 gives NaN/inf exactly where the reference's division does.
+PSQ_HD double rcp_nr(double d) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / d;
+#endif
+}
+PSQ_HD double rsqrt_nr(double d) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  double r = fma(-(h * y), y, 0.5);
+  y = fma(y, r, y);
+  r = fma(-(h * y), y, 0.5);
+  return fma(y, r, y);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
 PSQ_HD double ldg(const double* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -109,20 +138,33 @@ PSQ_HD void house_rows(double (&M)[R][C]) {
     const int kend = (TRIBLK > 0) ? ((TRIBLK + j + 1 < C) ? TRIBLK + j + 1 : C) : C;
     if (j + 1 >= kend) continue;
     const double alpha = M[j][j];
-    double sigma = 0.0;
+    // two partial sums halve the serial depth of the norm
+    double sigma = 0.0, sigma2 = 0.0;
     PSQ_UNROLL
-    for (int k = j + 1; k < kend; ++k) sigma = fma(M[j][k], M[j][k], sigma);
+    for (int k = j + 1; k < kend; k += 2) {
+      sigma = fma(M[j][k], M[j][k], sigma);
+      if (k + 1 < kend) sigma2 = fma(M[j][k + 1], M[j][k + 1], sigma2);
+    }
+    sigma += sigma2;
     const bool live = sigma != 0.0;
-    const double norm = sqrt(fma(alpha, alpha, sigma));
+    const double q = fma(alpha, alpha, sigma);
+    const double norm = live ? q * rsqrt_nr(q) : fabs(alpha);
     const double beta = live ? -copysign(norm, alpha) : alpha;
     const double v0 = alpha - beta;  // = alpha + sign(alpha) * norm : no cancellation
-    const double s = live ? 1.0 / (norm * (norm + fabs(alpha))) : 0.0;
+    const double s = live ? rcp_nr(fma(fabs(alpha), norm, q)) : 0.0;  // 1 / (norm (norm + |alpha|))
+    // the tail dot products do not depend on the norm: issued first so they overlap the
+    // rsqrt / rcp dependency chain; v0 and s enter last
+    double dots[(R - 1 > 0) ? R - 1 : 1];
     PSQ_UNROLL
     for (int i = j + 1; i < R; ++i) {
-      double d = M[i][j] * v0;
+      double d = 0.0;
       PSQ_UNROLL
       for (int k = j + 1; k < kend; ++k) d = fma(M[i][k], M[j][k], d);
-      d *= s;
+      dots[i - 1] = d;
+    }
+    PSQ_UNROLL
+    for (int i = j + 1; i < R; ++i) {
+      const double d = fma(M[i][j], v0, dots[i - 1]) * s;
       M[i][j] = fma(-d, v0, M[i][j]);
       PSQ_UNROLL
       for (int k = j + 1; k < kend; ++k) M[i][k] = fma(-d, M[j][k], M[i][k]);
@@ -142,16 +184,17 @@ PSQ_HD void tria_append(LAcc&& Lij, double (&W)[N][K]) {
     PSQ_UNROLL
     for (int k = 0; k < K; ++k) sigma = fma(W[j][k], W[j][k], sigma);
     const bool live = sigma != 0.0;
-    const double norm = sqrt(fma(alpha, alpha, sigma));
+    const double q = fma(alpha, alpha, sigma);
+    const double norm = live ? q * rsqrt_nr(q) : fabs(alpha);
     const double beta = live ? -copysign(norm, alpha) : alpha;
     const double v0 = alpha - beta;
-    const double s = live ? 1.0 / (norm * (norm + fabs(alpha))) : 0.0;
+    const double s = live ? rcp_nr(fma(fabs(alpha), norm, q)) : 0.0;
     PSQ_UNROLL
     for (int i = j + 1; i < N; ++i) {
-      double d = Lij(i, j) * v0;
+      double d = 0.0;  // dot product first (independent of the norm), v0 and s last
       PSQ_UNROLL
       for (int k = 0; k < K; ++k) d = fma(W[i][k], W[j][k], d);
-      d *= s;
+      d = fma(Lij(i, j), v0, d) * s;
       Lij(i, j) = fma(-d, v0, Lij(i, j));
       PSQ_UNROLL
       for (int k = 0; k < K; ++k) W[i][k] = fma(-d, W[j][k], W[i][k]);
@@ -173,19 +216,45 @@ struct StepPtrs {
   const double* R;   // [NY][NY] any square-root factor of the observation noise
   const double* c;   // [NY]
   const double* y;   // [NY]
+  template <int N> PSQ_HD double fF(int i, int j) const { return ldg(F + i * N + j); }
+  template <int N> PSQ_HD double fQ(int i, int j) const { return ldg(Q + i * N + j); }
+  PSQ_HD double fb(int i) const { return ldg(bq + i); }
+  template <int N> PSQ_HD double fH(int a, int k) const { return ldg(H + a * N + k); }
+  template <int NY> PSQ_HD double fR(int a, int q) const { return ldg(R + a * NY + q); }
+  PSQ_HD double fc(int a) const { return ldg(c + a); }
+  PSQ_HD double fy(int a) const { return ldg(y + a); }
+};
+
+// A time-invariant model passed BY VALUE as a kernel parameter: its entries are then constant-bank
+// operands of the FP64 instructions (no load instructions, no registers).  `y` stays a pointer.
+template <int N, int NY>
+struct ModelVals {
+  double F[N * N], Q[N * N], bq[N], H[NY * N], R[NY * NY], c[NY];
+};
+template <int N, int NY>
+struct StepVals {
+  const ModelVals<N, NY>& m;
+  const double* y;
+  template <int N_> PSQ_HD double fF(int i, int j) const { return m.F[i * N + j]; }
+  template <int N_> PSQ_HD double fQ(int i, int j) const { return m.Q[i * N + j]; }
+  PSQ_HD double fb(int i) const { return m.bq[i]; }
+  template <int N_> PSQ_HD double fH(int a, int k) const { return m.H[a * N + k]; }
+  template <int NY_> PSQ_HD double fR(int a, int q) const { return m.R[a * NY + q]; }
+  PSQ_HD double fc(int a) const { return m.c[a]; }
+  PSQ_HD double fy(int a) const { return ldg(y + a); }
 };
 
 // Shared by the Kalman update of both sweeps: given the predicted factor Np (lower, N x N,
 // read through Npij) build Psi = tria([[H Np, R], [Np, 0]])            _filtering.py:126-131
 // On return M2 holds Psi11 (rows/cols < NY), Psi21 (rows >= NY, cols < NY) and the posterior
 // factor (rows >= NY, cols >= NY, lower).
-template <int N, int NY, class NAcc>
-PSQ_HD void build_update(const StepPtrs& p, NAcc&& Npij, double (&M2)[NY + N][N + NY]) {
+template <int N, int NY, class P, class NAcc>
+PSQ_HD void build_update(const P& p, NAcc&& Npij, double (&M2)[NY + N][N + NY]) {
   PSQ_UNROLL
   for (int a = 0; a < NY; ++a) {
     double h[N];
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
+    for (int k = 0; k < N; ++k) h[k] = p.template fH<N>(a, k);
     PSQ_UNROLL
     for (int j = 0; j < N; ++j) {
       double acc = 0.0;
@@ -194,7 +263,7 @@ PSQ_HD void build_update(const StepPtrs& p, NAcc&& Npij, double (&M2)[NY + N][N 
       M2[a][j] = acc;
     }
     PSQ_UNROLL
-    for (int q = 0; q < NY; ++q) M2[a][N + q] = ldg(p.R + a * NY + q);
+    for (int q = 0; q < NY; ++q) M2[a][N + q] = p.template fR<NY>(a, q);
   }
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
@@ -208,7 +277,7 @@ PSQ_HD void build_update(const StepPtrs& p, NAcc&& Npij, double (&M2)[NY + N][N 
 template <int N, int NY>
 PSQ_HD void psi11_inv_diag(const double (&M2)[NY + N][N + NY], double (&inv)[NY]) {
   PSQ_UNROLL
-  for (int a = 0; a < NY; ++a) inv[a] = 1.0 / M2[a][a];
+  for (int a = 0; a < NY; ++a) inv[a] = rcp_nr(M2[a][a]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -218,18 +287,18 @@ PSQ_HD void psi11_inv_diag(const double (&M2)[NY + N][N + NY], double (&inv)[NY]
 // factor Z_k, to one square-root Kalman predict+update on (b, U), two N x N products on A and
 // a rank-NY append on Z.  (Equality with the generic combine is tested against the oracle.)
 // ---------------------------------------------------------------------------------------
-template <int N, int NY>
-PSQ_HD void filter_reduce_step(FElem<N>& acc, const StepPtrs& p) {
+template <int N, int NY, class P>
+PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
   double F[N][N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
 
   double mp[N], FA[N][N], M1[N][2 * N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
-    double s = ldg(p.bq + i);
+    double s = p.fb(i);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) s = fma(F[i][k], acc.b(k), s);
     mp[i] = s;
@@ -243,7 +312,7 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const StepPtrs& p) {
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], acc.U(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = ldg(p.Q + i * N + j);
+      M1[i][N + j] = p.template fQ<N>(i, j);
     }
   }
   house_rows<N, 2 * N, N>(M1);  // predicted factor = tria([F U | Q])
@@ -259,8 +328,8 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const StepPtrs& p) {
   for (int a = 0; a < NY; ++a) {
     double h[N];
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
-    double r = ldg(p.y + a) - ldg(p.c + a);
+    for (int k = 0; k < N; ++k) h[k] = p.template fH<N>(a, k);
+    double r = p.fy(a) - p.fc(a);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) r = fma(-h[k], mp[k], r);
     PSQ_UNROLL
@@ -313,17 +382,17 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const StepPtrs& p) {
 // where Phi11 is the predicted factor the update needs (sequential/_filtering.py:80-86).
 // Returns the log-likelihood increment (_filtering.py:149-154) computed from Psi11.
 // ---------------------------------------------------------------------------------------
-template <int N, int NY, bool SMOOTH>
-PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
+template <int N, int NY, bool SMOOTH, class P>
+PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
   double F[N][N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
   double mp[N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
-    double s = ldg(p.bq + i);
+    double s = p.fb(i);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) s = fma(F[i][k], x.m[k], s);
     mp[i] = s;
@@ -338,7 +407,7 @@ PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = ldg(p.Q + i * N + j);
+      M1[i][N + j] = p.template fQ<N>(i, j);
     }
   if (SMOOTH) {
     PSQ_UNROLL
@@ -358,7 +427,7 @@ PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
     // E = Phi21 Phi11^{-1}  (row-wise back substitution, _smoothing.py:83)
     double inv[N];
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) inv[j] = 1.0 / M1[j][j];
+    for (int j = 0; j < N; ++j) inv[j] = rcp_nr(M1[j][j]);
     PSQ_UNROLL
     for (int i = 0; i < N; ++i) {
       PSQ_UNROLL
@@ -383,9 +452,9 @@ PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
   double quad = 0.0, logdet = 0.0;
   PSQ_UNROLL
   for (int a = 0; a < NY; ++a) {
-    double r = ldg(p.y + a) - ldg(p.c + a);
+    double r = p.fy(a) - p.fc(a);
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) r = fma(-ldg(p.H + a * N + k), mp[k], r);
+    for (int k = 0; k < N; ++k) r = fma(-p.template fH<N>(a, k), mp[k], r);
     PSQ_UNROLL
     for (int q = 0; q < a; ++q) r = fma(-M2[a][q], rr[q], r);
     rr[a] = r * inv2[a];
@@ -406,18 +475,17 @@ PSQ_HD double kalman_step(Gauss<N>& x, const StepPtrs& p, SElem<N>* se) {
 
 // Smoothing element of step k from the filtered state alone (used by sweep 3, which
 // recomputes instead of re-reading 8(2N^2+N) bytes per step).            _smoothing.py:72-85
-template <int N>
-PSQ_HD void smoothing_element(const Gauss<N>& x, const double* Fp, const double* Qp, const double* bqp,
-                              SElem<N>& se) {
+template <int N, class P>
+PSQ_HD void smoothing_element(const Gauss<N>& x, const P& p, SElem<N>& se) {
   double F[N][N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) F[i][j] = ldg(Fp + i * N + j);
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
   double mp[N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
-    double s = ldg(bqp + i);
+    double s = p.fb(i);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) s = fma(F[i][k], x.m[k], s);
     mp[i] = s;
@@ -431,7 +499,7 @@ PSQ_HD void smoothing_element(const Gauss<N>& x, const double* Fp, const double*
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = ldg(Qp + i * N + j);
+      M1[i][N + j] = p.template fQ<N>(i, j);
     }
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
@@ -446,7 +514,7 @@ PSQ_HD void smoothing_element(const Gauss<N>& x, const double* Fp, const double*
   house_rows<N, N, N - 1>(B);
   double inv[N];
   PSQ_UNROLL
-  for (int j = 0; j < N; ++j) inv[j] = 1.0 / M1[j][j];
+  for (int j = 0; j < N; ++j) inv[j] = rcp_nr(M1[j][j]);
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
     PSQ_UNROLL
@@ -554,7 +622,7 @@ PSQ_HD void filtering_combine_core(const FElem<N>* e1full, const double (&b1)[N]
   // T1 = Xi11^{-1} U1^T   (N x N; U1^T is upper triangular so T1[i][j] needs k <= ... dense in general)
   double inv[N];
   PSQ_UNROLL
-  for (int i = 0; i < N; ++i) inv[i] = 1.0 / Xi[i][i];
+  for (int i = 0; i < N; ++i) inv[i] = rcp_nr(Xi[i][i]);
   double T1[N][N];
   PSQ_UNROLL
   for (int j = 0; j < N; ++j)
@@ -757,12 +825,12 @@ PSQ_HD void filtering_element(const StepPtrs& p, const double* m0, const double*
   for (int i = 0; i < N; ++i) {
     mz[i] = m0 ? m0[i] : 0.0;
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
   }
   double m1[N], M1[N][2 * N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
-    double s = ldg(p.bq + i);
+    double s = p.fb(i);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) s = fma(F[i][k], mz[k], s);
     m1[i] = s;
@@ -774,7 +842,7 @@ PSQ_HD void filtering_element(const StepPtrs& p, const double* m0, const double*
         for (int k = 0; k < N; ++k) u = fma(F[i][k], L0[k * N + j], u);
       }
       M1[i][j] = u;
-      M1[i][N + j] = ldg(p.Q + i * N + j);
+      M1[i][N + j] = p.template fQ<N>(i, j);
     }
   }
   house_rows<N, 2 * N, N>(M1);
@@ -788,12 +856,12 @@ PSQ_HD void filtering_element(const StepPtrs& p, const double* m0, const double*
   for (int a = 0; a < NY; ++a) {
     double h[N];
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) h[k] = ldg(p.H + a * N + k);
-    double ra = ldg(p.y + a) - ldg(p.c + a), rb = ra;
+    for (int k = 0; k < N; ++k) h[k] = p.template fH<N>(a, k);
+    double ra = p.fy(a) - p.fc(a), rb = ra;
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) {
       ra = fma(-h[k], m1[k], ra);
-      rb = fma(-h[k], ldg(p.bq + k), rb);
+      rb = fma(-h[k], p.fb(k), rb);
     }
     PSQ_UNROLL
     for (int q = 0; q < a; ++q) {
@@ -858,10 +926,10 @@ PSQ_HD double loglik_term(const StepPtrs& p, const double* m, const double* L) {
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
-    for (int j = 0; j < N; ++j) F[i][j] = ldg(p.F + i * N + j);
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
-    double s = ldg(p.bq + i);
+    double s = p.fb(i);
     PSQ_UNROLL
     for (int k = 0; k < N; ++k) s = fma(F[i][k], m[k], s);
     mp[i] = s;
@@ -871,7 +939,7 @@ PSQ_HD double loglik_term(const StepPtrs& p, const double* m, const double* L) {
       PSQ_UNROLL
       for (int k = 0; k < N; ++k) u = fma(F[i][k], L[k * N + j], u);
       M1[i][j] = u;
-      M1[i][N + j] = ldg(p.Q + i * N + j);
+      M1[i][N + j] = p.template fQ<N>(i, j);
     }
   }
   house_rows<N, 2 * N, N>(M1);
@@ -882,22 +950,22 @@ PSQ_HD double loglik_term(const StepPtrs& p, const double* m, const double* L) {
     for (int j = 0; j < N; ++j) {
       double s = 0.0;
       PSQ_UNROLL
-      for (int k = j; k < N; ++k) s = fma(ldg(p.H + a * N + k), M1[k][j], s);
+      for (int k = j; k < N; ++k) s = fma(p.template fH<N>(a, k), M1[k][j], s);
       S[a][j] = s;
     }
     PSQ_UNROLL
-    for (int q = 0; q < NY; ++q) S[a][N + q] = ldg(p.R + a * NY + q);
+    for (int q = 0; q < NY; ++q) S[a][N + q] = p.template fR<NY>(a, q);
   }
   house_rows<NY, N + NY, NY>(S);
   double rr[NY], quad = 0.0, logdet = 0.0;
   PSQ_UNROLL
   for (int a = 0; a < NY; ++a) {
-    double r = ldg(p.y + a) - ldg(p.c + a);
+    double r = p.fy(a) - p.fc(a);
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) r = fma(-ldg(p.H + a * N + k), mp[k], r);
+    for (int k = 0; k < N; ++k) r = fma(-p.template fH<N>(a, k), mp[k], r);
     PSQ_UNROLL
     for (int q = 0; q < a; ++q) r = fma(-S[a][q], rr[q], r);
-    rr[a] = r / S[a][a];
+    rr[a] = r * rcp_nr(S[a][a]);
     quad = fma(rr[a], rr[a], quad);
     logdet += log(fabs(S[a][a]));
   }

@@ -10,6 +10,7 @@ import ctypes
 import os
 from typing import Optional, Sequence
 
+import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -26,7 +27,8 @@ class PsqrtError(RuntimeError):
 class _Ssm(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("F", "cholQ", "b", "H", "cholR", "c")] + \
                [(n, ctypes.c_int64) for n in ("F_ts", "cholQ_ts", "b_ts", "H_ts", "cholR_ts", "c_ts")] + \
-               [(n, ctypes.c_int64) for n in ("F_bs", "cholQ_bs", "b_bs", "H_bs", "cholR_bs", "c_bs")]
+               [(n, ctypes.c_int64) for n in ("F_bs", "cholQ_bs", "b_bs", "H_bs", "cholR_bs", "c_bs")] + \
+               [(n, ctypes.c_void_p) for n in ("hF", "hcholQ", "hb", "hH", "hcholR", "hc")]
 
 
 class Plan(ctypes.Structure):
@@ -39,8 +41,11 @@ EXPORTS = (
     "psqrt_filter_smoother", "psqrt_smoother", "psqrt_filter_reduce", "psqrt_carry_filter", "psqrt_filter_apply",
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
-    "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched",
+    "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
 )
+
+MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
+LIN_EXTENDED, LIN_SLR = 0, 1
 
 
 def lib_path() -> str:
@@ -117,10 +122,15 @@ def _require(nx: int, ny: int):
 
 class LinearizedSSM:
     """Per-step linearised model (F, cholQ, b, H, cholR, c): each entry is a tensor whose leading
-    dims are [] (shared), [T] (per step) or [B, T] / [B] (per sequence)."""
+    dims are [] (shared), [T] (per step) or [B, T] / [B] (per sequence).
 
-    def __init__(self, F, cholQ, b, H=None, cholR=None, c=None):
+    `host`: optional {name: numpy array} mirrors of time-invariant entries (also picked up from a
+    `_psqrt_host` attribute on the tensors).  With mirrors for every entry of a fully shared model the
+    kernels take the model by value (constant-bank operands) instead of loading it per step."""
+
+    def __init__(self, F, cholQ, b, H=None, cholR=None, c=None, host=None):
         self.F, self.cholQ, self.b, self.H, self.cholR, self.c = F, cholQ, b, H, cholR, c
+        self.host = dict(host or {})
 
     def struct(self, T: int, batch: int, keep: list) -> _Ssm:
         s = _Ssm()
@@ -152,6 +162,12 @@ class LinearizedSSM:
             setattr(s, name, _ptr(t).value)
             setattr(s, name + "_ts", ts)
             setattr(s, name + "_bs", bs)
+            h = self.host.get(name, getattr(getattr(self, name), "_psqrt_host", None))
+            if h is not None and len(lead) == 0:
+                h = np.ascontiguousarray(h, dtype=np.float64)
+                if h.shape == tuple(t.shape):
+                    keep.append(h)
+                    setattr(s, "h" + name, h.ctypes.data)
         return s
 
 
@@ -463,3 +479,49 @@ def chol_update_many(L: torch.Tensor, V: torch.Tensor, alpha: float) -> torch.Te
                                                ctypes.c_int64(Lb.shape[0]), _stream())
         _check(rc, "psqrt_chol_update_batched")
     return Lb.reshape(*lead, n, n)
+
+
+_points_cache = {}
+
+
+def _device_points(xi, wm, wc, device):
+    """Sigma-point tables are tiny constants per (rule, n): uploaded once per device."""
+    key = (xi.tobytes(), wm.tobytes(), wc.tobytes(), str(device))
+    hit = _points_cache.get(key)
+    if hit is None:
+        hit = tuple(torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device) for a in (xi, wm, wc))
+        _points_cache[key] = hit
+    return hit
+
+
+def linearize_builtin(model_id: int, params, lin_id: int, n_in: int, n_out: int, conditional: bool,
+                      nom_m: torch.Tensor, nom_L: Optional[torch.Tensor] = None, m_q: Optional[torch.Tensor] = None,
+                      chol_q: Optional[torch.Tensor] = None, points=None):
+    """psqrt_linearize_builtin on [..., n] nominal means (and [..., n, n] factors for SLR).
+    Returns (F [..., d, n], chol [..., d, d] or None, b [..., d])."""
+    lib = load()
+    lead = nom_m.shape[:-1]
+    dev = nom_m.device
+    m = nom_m.reshape(-1, n_in).contiguous()
+    count = m.shape[0]
+    F = torch.empty((count, n_out, n_in), dtype=torch.float64, device=dev)
+    b = torch.empty((count, n_out), dtype=torch.float64, device=dev)
+    need_chol = conditional or lin_id == LIN_SLR
+    chol = torch.empty((count, n_out, n_out), dtype=torch.float64, device=dev) if need_chol else None
+    L = xi = wm = wc = None
+    P = 0
+    if lin_id == LIN_SLR:
+        L = nom_L.expand(*lead, n_in, n_in).reshape(-1, n_in, n_in).contiguous()
+        xi, wm, wc = _device_points(*points, dev)
+        P = xi.shape[0]
+    pars = (ctypes.c_double * len(params))(*[float(v) for v in params])
+    if count > 0:
+        with torch.cuda.device(dev):
+            rc = lib.psqrt_linearize_builtin(int(model_id), pars, int(lin_id), _ptr(xi), _ptr(wm), _ptr(wc), int(P),
+                                             _ptr(m), _ptr(L), ctypes.c_int64(count),
+                                             _ptr(m_q.contiguous() if m_q is not None else None),
+                                             _ptr(chol_q.contiguous() if chol_q is not None else None),
+                                             _ptr(F), _ptr(chol), _ptr(b), _stream())
+        _check(rc, "psqrt_linearize_builtin")
+    return (F.reshape(*lead, n_out, n_in), chol.reshape(*lead, n_out, n_out) if need_chol else None,
+            b.reshape(*lead, n_out))

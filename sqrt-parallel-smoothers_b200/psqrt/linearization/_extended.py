@@ -16,14 +16,18 @@ def linearize(model, x):
         require_sqrt(q)
         builtin = getattr(f, "_psqrt_builtin", None)
         if builtin is not None:
-            return builtin.extended(x, q)
+            out = builtin.extended(x, q)
+            if out is not None:
+                return out
         m_x = x.mean
         res, F_x = value_and_jac(f, m_x)
         return F_x, q.chol, res - mv(F_x, m_x) + q.mean
     c_m, c_chol = model
     builtin = getattr(c_m, "_psqrt_builtin", None)
     if builtin is not None:
-        return builtin.extended_conditional(x)
+        out = builtin.extended_conditional(x)
+        if out is not None:
+            return out
     m = x.mean
     res, F = value_and_jac(c_m, m)
     return F, apply_fn(c_chol, m), res - mv(F, m)

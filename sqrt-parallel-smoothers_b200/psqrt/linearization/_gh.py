@@ -46,7 +46,9 @@ def linearize(model, x, order: int = 3):
     n = x.mean.shape[-1]
     wm, wc, xi = _gauss_hermite_weights(n, order)
     if builtin is not None and hasattr(builtin, "slr"):
-        return builtin.slr(model, x, xi, wm, wc)
+        out = builtin.slr(model, x, xi, wm, wc)
+        if out is not None:
+            return out
     dev = x.mean.device
     xi_t, wm_t, wc_t = (torch.as_tensor(a, dtype=torch.float64, device=dev) for a in (xi, wm, wc))
     if isinstance(model, FunctionalModel):

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -27,7 +28,15 @@ def _device():
 
 
 def _t(x, dev):
-    return torch.as_tensor(x, dtype=torch.float64).to(dev)
+    """-> fp64 tensor on `dev`.  Inputs that live on the host keep a NumPy mirror (`_psqrt_host`) so that
+    small time-invariant model matrices can travel to the kernels by value (psqrt._lib.LinearizedSSM)."""
+    if torch.is_tensor(x) and x.is_cuda:
+        return x.to(dev, dtype=torch.float64)
+    host = np.asarray(x.detach().cpu().numpy() if torch.is_tensor(x) else x, dtype=np.float64)
+    t = torch.as_tensor(host).to(dev)
+    if host.size <= 4096:
+        t._psqrt_host = host
+    return t
 
 
 def _mvn(x, dev):

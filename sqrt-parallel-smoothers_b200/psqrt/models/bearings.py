@@ -6,6 +6,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import _lib
+
 
 def make_transition_function(dt: float):
     """x = (px, py, vx, vy, w).  For |w| < 1e-6 the reference's lax.cond takes sin(wt)/w -> dt and
@@ -53,7 +55,8 @@ def make_transition_function(dt: float):
 
     f._psqrt_batched = True
     f._psqrt_value_and_jac = value_and_jac
-    f._psqrt_model = ("ct_transition", (float(dt),))
+    from ._builtin import Builtin
+    f._psqrt_builtin = Builtin(_lib.MODEL_CT_TRANSITION, [float(dt)], 5, 5)
     return f
 
 
@@ -76,7 +79,8 @@ def make_observation_function(s1, s2):
 
     f._psqrt_batched = True
     f._psqrt_value_and_jac = value_and_jac
-    f._psqrt_model = ("bearings_observation", (s1[0], s1[1], s2[0], s2[1]))
+    from ._builtin import Builtin
+    f._psqrt_builtin = Builtin(_lib.MODEL_BEARINGS_OBSERVATION, [s1[0], s1[1], s2[0], s2[1]], 5, 2)
     return f
 
 

@@ -16,7 +16,9 @@ class _LinearBuiltin:
         self.M = M
 
     def _M(self, like):
-        return torch.as_tensor(self.M, dtype=torch.float64).to(like.device)
+        t = torch.as_tensor(self.M, dtype=torch.float64).to(like.device)
+        t._psqrt_host = np.asarray(self.M.detach().cpu().numpy(), dtype=np.float64)   # host mirror (by-value path)
+        return t
 
     def extended(self, x: MVNSqrt, q: MVNSqrt):
         return self._M(x.mean), q.chol, q.mean

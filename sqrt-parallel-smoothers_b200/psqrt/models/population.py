@@ -36,6 +36,10 @@ def make_parameters(lam: float, Q):
         return torch.sqrt(lam * torch.exp(x))[..., None]
 
     chol_o._psqrt_batched = True
+    from .. import _lib
+    from ._builtin import Builtin
+    mean_t._psqrt_builtin = Builtin(_lib.MODEL_RICKER_TRANSITION, [float(torch.sqrt(Q_t).item())], 1, 1, conditional=True)
+    mean_o._psqrt_builtin = Builtin(_lib.MODEL_POISSON_OBSERVATION, [float(lam)], 1, 1, conditional=True)
     return ConditionalMomentsModel(mean_t, chol_t), ConditionalMomentsModel(mean_o, chol_o)
 
 

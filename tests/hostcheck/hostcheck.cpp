@@ -114,7 +114,7 @@ int pass(const HSsm& a, long long T, int K, const double* m0, const double* L0, 
       Gauss<N> xf; load_dense<N>(fm + k * N, fL + k * N * N, xf);
       SElem<N> se;
       StepPtrs p = sp(a, k);
-      smoothing_element<N>(xf, p.F, p.Q, p.bq, se);
+      smoothing_element<N>(xf, p, se);
       smoothing_apply<N>(xs, se);
       store_dense<N>(sm + k * N, sL + k * N * N, xs);
     }

@@ -73,6 +73,33 @@ def test_pass_vs_oracle_time_varying(n, ny, T, K):
     assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
 
 
+@pytest.mark.parametrize("n,ny,T,K", [(4, 2, 1000, 0), (5, 2, 333, 4), (1, 1, 100, 3), (2, 3, 77, 5), (8, 4, 130, 0),
+                                      (6, 4, 257, 3), (3, 1, 33, 1)])
+def test_pass_by_value_model(n, ny, T, K):
+    """Time-invariant model carried by value in the kernel parameters (host mirrors given): same
+    results as the pointer path and as the oracle; also through the public API with NumPy inputs."""
+    import psqrt
+    from psqrt import _lib
+    from psqrt._lib import LinearizedSSM
+    from psqrt.models import lgssm
+    case = lgssm_case(n, ny, T, seed=100 * n + ny)
+    names = ("F", "cholQ", "b", "H", "cholR", "c")
+    ssm = LinearizedSSM(*[_g(case[k]) for k in names], host={k: case[k] for k in names})
+    fm, fL, sm, sL, ell = _lib.filter_smoother(ssm, _g(case["ys"]), _g(case["m0"]), _g(case["L0"]), smooth=True,
+                                               loglik=True, chunk_len=K)
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    _check_traj("filtered", fm, fL, ofm, ofc)
+    _check_traj("smoothed", sm, sL, osm, osc)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+    sm2, sL2 = _lib.smoother(LinearizedSSM(ssm.F, ssm.cholQ, ssm.b, host=ssm.host), fm, fL, chunk_len=K)
+    _check_traj("smoother-only", sm2, sL2, osm, osc)
+    # public API, NumPy inputs: mirrors are attached automatically
+    tm = psqrt.FunctionalModel(lgssm.transition_function(case["F"]), psqrt.MVNSqrt(case["b"], case["cholQ"]))
+    om = psqrt.FunctionalModel(lgssm.observation_function(case["H"]), psqrt.MVNSqrt(case["c"], case["cholR"]))
+    res = psqrt.filter_smoother(case["ys"], psqrt.MVNSqrt(case["m0"], case["L0"]), tm, om, psqrt.linearization.extended)
+    _check_traj("api", res.mean, res.chol, osm, osc)
+
+
 def test_pass_vs_sequential_oracle():
     """Second oracle: the reference's sequential sqrt filter / smoother (sequential/_filtering.py, _smoothing.py)."""
     from psqrt import _lib
@@ -310,6 +337,48 @@ def test_methods_api_lgssm(dim_x, dim_y, lin_name):
     oit2, oell2 = O.iterated_smoothing(case["ys"], ox0, otm, oom, olin, None, True, return_loglikelihood=True)
     _check_traj("iterated-default", it2.mean, it2.chol, oit2.mean, oit2.chol, tol=1e-8)
     assert abs(ell2.item() - oell2) <= TOL_ELL * abs(oell2)
+
+
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+def test_builtin_linearization_kernels(lin_name):
+    """psqrt_linearize_builtin (csrc/psqrt_models.cu) against the oracle's linearization
+    (linearization/_extended.py, _sigma_points.py, _cubature.py, _gh.py) at random nominal points,
+    including a |w| < 1e-6 turn rate (the lax.cond branch of bearings_utils.py:24-37)."""
+    import psqrt
+    from psqrt.models import bearings, population
+    rng = np.random.RandomState(11)
+    T = 301
+    nm = rng.randn(T, 5) * np.array([2.0, 2.0, 3.0, 3.0, 1.0])
+    nm[7, 4] = 1e-8
+    nL = 0.3 * (np.tril(rng.rand(T, 5, 5)) + np.eye(5))
+    Q, R, obs_f, trans_f = bearings.make_parameters(0.01, 0.1, 0.5, 0.01, np.array([-1.5, 0.5]), np.array([1.0, 1.0]))
+    _, _, oobs, otrans = O.bearings_make_parameters(0.01, 0.1, 0.5, 0.01, np.array([-1.5, 0.5]), np.array([1.0, 1.0]))
+    cQ, cR = np.linalg.cholesky(Q), np.linalg.cholesky(R)
+    mq, mr = 0.1 * rng.randn(5), 0.1 * rng.randn(2)
+    lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+    x = psqrt.MVNSqrt(_g(nm), _g(nL))
+    ox = O.MVNSqrt(nm, nL)
+    for f, of, m_q, c_q in ((trans_f, otrans, mq, cQ), (obs_f, oobs, mr, cR)):
+        assert hasattr(f, "_psqrt_builtin")
+        F, ch, b = lin(psqrt.FunctionalModel(f, psqrt.MVNSqrt(_g(m_q), _g(c_q))), x)
+        oF, och, ob = olin(O.FunctionalModel(of, O.MVNSqrt(m_q, c_q)), ox)
+        assert rel_err(F.cpu().numpy(), oF) < TOL and rel_err(b.cpu().numpy(), ob) < TOL
+        chn = np.broadcast_to(ch.cpu().numpy(), och.shape)
+        # the residual covariance Phi + Q - F P F^T is a difference of nearly equal matrices for SLR
+        # (_sigma_points.py:77-78): the meaningful scale of its error is that of the terms, F P F^T
+        FL = oF @ nL
+        scale = max(float(np.abs(LLt(och)).max()), float(np.abs(FL @ np.swapaxes(FL, -1, -2)).max()))
+        err = float(np.abs(LLt(chn) - LLt(och)).max()) / scale
+        assert err < TOL, f"{lin_name}: residual covariance error {err:.3e} (scale {scale:.3e})"
+    pm = np.log(7.0) + 0.5 * rng.randn(T, 1)
+    pL = 0.05 + 0.5 * rng.rand(T, 1, 1)
+    tmod, omod = population.make_parameters(10.0, np.array([[0.09]]))
+    otmod, oomod = O.population_model(10.0, np.array([[0.09]]))
+    for mod, omodel in ((tmod, otmod), (omod, oomod)):
+        F, ch, b = lin(mod, psqrt.MVNSqrt(_g(pm), _g(pL)))
+        oF, och, ob = olin(omodel, O.MVNSqrt(pm, pL))
+        assert rel_err(F.cpu().numpy(), oF) < TOL and rel_err(b.cpu().numpy(), ob) < TOL
+        assert rel_err(LLt(ch.cpu().numpy()), LLt(och)) < TOL
 
 
 def _bearings_setup(T, seed=0):
