@@ -338,12 +338,18 @@ def run_psqrt(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = share[dom] * T / (stages[dom] * 1e-3) / 1e9
-        pass_achieved = algorithmic_bytes_per_step(NX) * (T / (ms_per_step * 1e-3)) / 1e9 if world == 1 else None
+        # whole pass, per GPU: B(n) bytes per step over the time of the complete pass
+        pass_achieved = algorithmic_bytes_per_step(NX) * (T / (ms_per_step * 1e-3)) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_step": share[dom], "stage_ms": stages,
                     "whole_pass": {"algorithmic_bytes_per_step": algorithmic_bytes_per_step(NX),
-                                   "achieved": pass_achieved, "frac": (pass_achieved / peak) if pass_achieved else None}}
+                                   "achieved": pass_achieved, "frac": pass_achieved / peak,
+                                   "note": "per GPU; B(n) = 8(7n^2+5n) canonical bytes per step / time of the whole pass"}}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) -----------------------------
     cpu_baseline = None

@@ -46,6 +46,9 @@ extern "C" {
  * step (parsmooth/parallel/_filtering.py:117-119):
  *     x_{k+1} = F_k x_k + b_k + N(0, cholQ_k cholQ_k^T)        F [nx,nx] cholQ [nx,nx] b [nx]
  *     y_k     = H_k x_{k+1} + c_k + N(0, cholR_k cholR_k^T)    H [ny,nx] cholR [ny,ny] c [ny]
+ * cholQ must be LOWER TRIANGULAR in the pass / staged / smoother entry points (entries above its diagonal
+ * are ignored; any other square root of Q is first passed through psqrt_tria_batched by the caller) --
+ * that triangle shortens every reflector of the predict step; cholR may be any square root.
  * *_ts is the stride in doubles between consecutive time steps (0 = time-invariant),
  * *_bs the stride between sequences of a batch (0 = shared).  H, cholR, c may be NULL for
  * smoother-only calls. */

@@ -27,6 +27,10 @@ namespace {
 
 constexpr int N = PSQ_N;
 
+// The by-value (constant-bank) model variants double the number of sweep instantiations; they are
+// compiled for the small state dimensions where they pay (nx <= 5) to keep build times in check.
+constexpr bool kByValue = (PSQ_N <= 5);
+
 // Fill a by-value model (kernel parameter) from the host mirrors.
 template <int NY>
 SrcVal<N, NY> make_src_val(const HostModel& h, const SSMArgs& a) {
@@ -47,10 +51,14 @@ template <int NY>
 struct NYImpl {
   static void filter_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                             double* chunk_pref, double* warp_tot, unsigned int* counter, cudaStream_t st) {
-    if (hm) {
-      k_filter_reduce<N, NY, SrcVal<N, NY>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<NY>(*hm, a), T, K, Ppad,
-                                                                                   chunk_pref, warp_tot, counter);
-    } else {
+    if constexpr (kByValue) {
+      if (hm) {
+        k_filter_reduce<N, NY, SrcVal<N, NY>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<NY>(*hm, a), T, K,
+                                                                                     Ppad, chunk_pref, warp_tot, counter);
+        return;
+      }
+    }
+    {
       k_filter_reduce<N, NY, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, chunk_pref, warp_tot,
                                                                             counter);
     }
@@ -83,13 +91,15 @@ struct NYImpl {
 #define PSQ_FA(SM, SRCV)                                                                                             \
   filter_apply_t<SM>(SRCV, T, K, Ppad, B, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot,  \
                      ell_part, counter_s, selems, st)
-    if (hm) {
-      const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
-      if (smooth) PSQ_FA(true, sv); else PSQ_FA(false, sv);
-    } else {
-      const SrcPtr sp{a};
-      if (smooth) PSQ_FA(true, sp); else PSQ_FA(false, sp);
+    if constexpr (kByValue) {
+      if (hm) {
+        const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
+        if (smooth) PSQ_FA(true, sv); else PSQ_FA(false, sv);
+        return;
+      }
     }
+    const SrcPtr sp{a};
+    if (smooth) PSQ_FA(true, sp); else PSQ_FA(false, sp);
 #undef PSQ_FA
   }
   static void filter_elements(const SSMArgs& a, long long T, long long B, const double* m0, const double* L0,
@@ -137,11 +147,8 @@ void mid_smooth(double* items, long long M, long long B, double* groups, unsigne
 void smooth_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                    const double* fm, const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter,
                    double* selems, cudaStream_t st) {
-  if (hm)
-    k_smooth_reduce<N, SrcVal<N, 1>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<1>(*hm, a), T, K, Ppad, fm, fL,
-                                                                            chunk_suf, warp_stot, counter, selems);
-  else
-    k_smooth_reduce<N, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, fm, fL, chunk_suf,
+  (void)hm;  // the standalone smoother is not a hot path: pointer model only
+  k_smooth_reduce<N, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, fm, fL, chunk_suf,
                                                                       warp_stot, counter, selems);
 }
 template <int NN>

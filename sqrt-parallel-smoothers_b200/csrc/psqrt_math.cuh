@@ -312,10 +312,10 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], acc.U(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = p.template fQ<N>(i, j);
+      M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
     }
   }
-  house_rows<N, 2 * N, N>(M1);  // predicted factor = tria([F U | Q])
+  house_rows<N, 2 * N, N, N>(M1);  // predicted factor = tria([F U | Q]); Q's triangle shortens every reflector
 
   double M2[NY + N][N + NY];
   build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
@@ -407,7 +407,7 @@ PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = p.template fQ<N>(i, j);
+      M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
     }
   if (SMOOTH) {
     PSQ_UNROLL
@@ -415,7 +415,7 @@ PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
       PSQ_UNROLL
       for (int j = 0; j < 2 * N; ++j) M1[RR - N + i][j] = (j <= i) ? x.Lc(i, j) : 0.0;
   }
-  house_rows<RR, 2 * N, N>(M1);
+  house_rows<RR, 2 * N, N, N>(M1);
   if (SMOOTH) {
     // D = tria(bottom-right block)
     double B[N][N];
@@ -499,13 +499,13 @@ PSQ_HD void smoothing_element(const Gauss<N>& x, const P& p, SElem<N>& se) {
       PSQ_UNROLL
       for (int k = j; k < N; ++k) u = fma(F[i][k], x.Lc(k, j), u);
       M1[i][j] = u;
-      M1[i][N + j] = p.template fQ<N>(i, j);
+      M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
     }
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
     for (int j = 0; j < 2 * N; ++j) M1[N + i][j] = (j <= i) ? x.Lc(i, j) : 0.0;
-  house_rows<2 * N, 2 * N, N>(M1);
+  house_rows<2 * N, 2 * N, N, N>(M1);
   double B[N][N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)

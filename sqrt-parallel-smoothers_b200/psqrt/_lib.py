@@ -462,7 +462,9 @@ def tria(A: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(A.device):
             rc = lib.psqrt_tria_batched(_ptr(Ab), _ptr(L), rows, cols, ctypes.c_int64(Ab.shape[0]), _stream())
         _check(rc, "psqrt_tria_batched")
-    return L.reshape(*lead, rows, rows)
+    L = L.reshape(*lead, rows, rows)
+    L._psqrt_lower = True
+    return L
 
 
 def chol_update_many(L: torch.Tensor, V: torch.Tensor, alpha: float) -> torch.Tensor:
@@ -478,7 +480,9 @@ def chol_update_many(L: torch.Tensor, V: torch.Tensor, alpha: float) -> torch.Te
             rc = lib.psqrt_chol_update_batched(_ptr(Lb), _ptr(Vb), n, k, ctypes.c_double(alpha),
                                                ctypes.c_int64(Lb.shape[0]), _stream())
         _check(rc, "psqrt_chol_update_batched")
-    return Lb.reshape(*lead, n, n)
+    Lb = Lb.reshape(*lead, n, n)
+    Lb._psqrt_lower = True            # _utils.py:79: the update zeroes the upper triangle
+    return Lb
 
 
 _points_cache = {}
@@ -523,5 +527,7 @@ def linearize_builtin(model_id: int, params, lin_id: int, n_in: int, n_out: int,
                                              _ptr(chol_q.contiguous() if chol_q is not None else None),
                                              _ptr(F), _ptr(chol), _ptr(b), _stream())
         _check(rc, "psqrt_linearize_builtin")
-    return (F.reshape(*lead, n_out, n_in), chol.reshape(*lead, n_out, n_out) if need_chol else None,
-            b.reshape(*lead, n_out))
+    if need_chol:
+        chol = chol.reshape(*lead, n_out, n_out)
+        chol._psqrt_lower = True      # written by the kernel with an exactly zero upper triangle
+    return F.reshape(*lead, n_out, n_in), chol, b.reshape(*lead, n_out)

@@ -73,9 +73,26 @@ def _slice(nominal, sl):
     return MVNSqrt(nominal.mean[sl], nominal.chol[sl])
 
 
+def _lower(chol):
+    """The kernels read only the lower triangle of cholQ: any other square root of the process noise is
+    triangularised first (tria, parsmooth/_utils.py:22-24; L L^T is unchanged)."""
+    if getattr(chol, "_psqrt_lower", False):
+        return chol
+    host = getattr(chol, "_psqrt_host", None)
+    if host is not None:
+        if not np.any(np.triu(host, 1)):
+            return chol
+    elif chol.dim() == 2 and not bool((torch.triu(chol, 1) != 0).any()):
+        return chol
+    out = _lib.tria(chol)
+    out._psqrt_lower = True
+    return out
+
+
 def _linearize(lin, transition_model, observation_model, nominal):
     """transition at nominal[:-1], observation at nominal[1:] (parallel/_filtering.py:103-104,117-119)."""
     F, cholQ, b = lin(transition_model, _slice(nominal, slice(None, -1)))
+    cholQ = _lower(cholQ)
     if observation_model is None:
         return LinearizedSSM(F, cholQ, b)
     H, cholR, c = lin(observation_model, _slice(nominal, slice(1, None)))

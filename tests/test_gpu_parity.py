@@ -381,6 +381,30 @@ def test_builtin_linearization_kernels(lin_name):
         assert rel_err(LLt(ch.cpu().numpy()), LLt(och)) < TOL
 
 
+def test_non_triangular_noise_factors():
+    """cholQ / cholR given as arbitrary (non-triangular) square roots, like the reference allows: the host
+    layer triangularises cholQ before the kernels read its lower triangle; results depend on Q Q^T only."""
+    import psqrt
+    from psqrt.models import lgssm
+    T = 150
+    case = lgssm_case(4, 2, T, seed=21)
+    rng = np.random.RandomState(2)
+    Oq, _ = np.linalg.qr(rng.randn(4, 4))
+    Or, _ = np.linalg.qr(rng.randn(2, 2))
+    sqQ, sqR = case["cholQ"] @ Oq, case["cholR"] @ Or                 # same Q, R; dense factors
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    for dev_inputs in (False, True):
+        conv = _g if dev_inputs else (lambda a: a)
+        tm = psqrt.FunctionalModel(lgssm.transition_function(case["F"]), psqrt.MVNSqrt(conv(case["b"]), conv(sqQ)))
+        om = psqrt.FunctionalModel(lgssm.observation_function(case["H"]), psqrt.MVNSqrt(conv(case["c"]), conv(sqR)))
+        x0 = psqrt.MVNSqrt(conv(case["m0"]), conv(case["L0"]))
+        filt, ell = psqrt.filtering(case["ys"], x0, tm, om, psqrt.linearization.extended, None, True, True)
+        smo = psqrt.filter_smoother(case["ys"], x0, tm, om, psqrt.linearization.extended)
+        _check_traj("filtered", filt.mean, filt.chol, ofm, ofc)
+        _check_traj("smoothed", smo.mean, smo.chol, osm, osc)
+        assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+
+
 def _bearings_setup(T, seed=0):
     from psqrt.models import bearings
     s1, s2, r, dt, qc, qw = np.array([-1.5, 0.5]), np.array([1.0, 1.0]), 0.5, 0.01, 0.01, 0.1
