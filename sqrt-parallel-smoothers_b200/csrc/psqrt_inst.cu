@@ -79,6 +79,17 @@ struct NYImpl {
         return;
       }
     }
+    if constexpr (N % 2 == 1) {
+      // pair-staged factor stream: pairs start at even indices, so every sequence must start 16-byte aligned
+      if (aligned16(fL) && (B == 1 || (T + 1) % 2 == 0)) {
+        const size_t smem = tma::CfgOdd<N>::smem_bytes(kBlock);
+        auto kern = k_filter_apply_tma_odd<N, NY, SMOOTH, SRC>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm,
+                                                       fL, chunk_suf, warp_stot, ell_part, counter_s, selems);
+        return;
+      }
+    }
     k_filter_apply<N, NY, SMOOTH, SRC><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
         src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s,
         selems);
@@ -161,6 +172,16 @@ void smooth_apply_t(long long T, int K, long long Ppad, long long B, const doubl
     if (al(sm) && al(sL)) {   // staged loads + stores (TMA bulk copies)
       const size_t smem = tma::Cfg<NN>::smem_bytes(kBlock);
       auto kern = k_smooth_apply_tma<NN>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
+                                                     selems, sm, sL, write_terminal);
+      return;
+    }
+  }
+  if constexpr (NN % 2 == 1) {
+    if ((reinterpret_cast<uintptr_t>(sL) & 15u) == 0 && (B == 1 || (T + 1) % 2 == 0)) {
+      const size_t smem = tma::CfgOdd<NN>::smem_bytes(kBlock);
+      auto kern = k_smooth_apply_tma_odd<NN>;
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
                                                      selems, sm, sL, write_terminal);

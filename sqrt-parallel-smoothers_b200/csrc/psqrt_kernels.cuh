@@ -600,6 +600,160 @@ k_filter_apply_tma(const __grid_constant__ SRC src, long long T, int K, long lon
   tma::bulk_wait<0>();
 }
 
+// ---- odd N: pair-staged factor stream (psqrt_tma.cuh, CfgOdd) --------------------------------
+template <int N>
+struct OddFactorStage {
+  double* slice;        // this lane's shared-memory slice: [NBUF][2][N*N]
+  double* gm;           // trajectory means   [*, N]
+  double* gL;           // trajectory factors [*, N, N]
+  long long first, last;  // inclusive index range this thread writes
+  int t;                // tiles handed to TMA so far
+
+  __device__ __forceinline__ void direct(long long idx, const Gauss<N>& x) const {
+    double* L = gL + idx * N * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) L[i * N + j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  }
+  __device__ __forceinline__ void stage(int slot, const Gauss<N>& x) const {
+    double* b = slice + (t % tma::CfgOdd<N>::NBUF) * tma::CfgOdd<N>::PAIR + slot * N * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) b[i * N + j] = (j <= i) ? x.Lc(i, j) : 0.0;
+  }
+  __device__ __forceinline__ void flush(long long even_idx) {
+    tma::fence_proxy_async();
+    tma::bulk_store(gL + even_idx * N * N, slice + (t % tma::CfgOdd<N>::NBUF) * tma::CfgOdd<N>::PAIR,
+                    (unsigned)(tma::CfgOdd<N>::PAIR * sizeof(double)));
+    tma::bulk_commit();
+    ++t;
+  }
+  // ASC: indices arrive in increasing order; otherwise decreasing.
+  template <bool ASC>
+  __device__ __forceinline__ void put(long long idx, const Gauss<N>& x) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) gm[idx * N + i] = x.m[i];
+    const bool odd = idx & 1;
+    const bool paired = odd ? (idx - 1 >= first) : (idx + 1 <= last);
+    if (!paired) {
+      direct(idx, x);
+      return;
+    }
+    const bool opens = ASC ? !odd : odd;  // first record of its pair to arrive
+    if (opens) tma::bulk_wait_read<tma::CfgOdd<N>::NBUF - 1>();  // the buffer's previous tile has been drained
+    stage(odd ? 1 : 0, x);
+    if (!opens) flush(odd ? idx - 1 : idx);
+  }
+};
+
+template <int N>
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
+k_smooth_apply_tma_odd(long long T, int K, long long Ppad,
+                       const double* __restrict__ carry_m, const double* __restrict__ carry_L,
+                       long long carry_mstride, long long carry_Lstride,
+                       const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
+                       const double* __restrict__ group_suf, const double* __restrict__ selems,
+                       double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  if (k0 >= k1) return;
+  double* smS = sm + seq * (T + 1) * N;
+  double* sLS = sL + seq * (T + 1) * N * N;
+  OddFactorStage<N> st{reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * tma::CfgOdd<N>::LANE, smS, sLS, k0,
+                       k1 - 1, 0};
+  SElem<N> se;
+  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
+  Gauss<N> xs;
+  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
+  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
+  {
+    SElem<N> e;
+    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);
+    smoothing_apply<N>(xs, e);
+    soa_load(warp_suf, seq, Mw, c / 32, e);
+    smoothing_apply<N>(xs, e);
+    soa_load(chunk_suf, seq, Ppad, c, e);
+    smoothing_apply<N>(xs, e);
+  }
+#pragma unroll 1
+  for (long long k = k1 - 1; k >= k0; --k) {
+    SElem<N> nxt;
+    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);
+    smoothing_apply<N>(xs, se);
+    st.template put<false>(k, xs);
+    se = nxt;
+  }
+  tma::bulk_wait<0>();
+}
+
+template <int N, int NY, bool SMOOTH, class SRC>
+__global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
+k_filter_apply_tma_odd(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
+                       const double* __restrict__ carry_m, const double* __restrict__ carry_L,
+                       const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
+                       const double* __restrict__ group_pref,
+                       double* __restrict__ fm, double* __restrict__ fL,
+                       double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
+                       unsigned int* __restrict__ counter, double* __restrict__ selems) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long seq = blockIdx.y;
+  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long Mw = Ppad / 32;
+  const long long k0 = c * K;
+  const long long k1 = (k0 + K < T) ? k0 + K : T;
+  if (SMOOTH && c == 0) counter[seq] = 0u;
+  Gauss<N> x;
+  load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
+  {
+    FElem<N> e;
+    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
+    filtering_apply<N>(x, e);
+    soa_load(warp_pref, seq, Mw, c / 32, e);
+    filtering_apply<N>(x, e);
+    soa_load(chunk_pref, seq, Ppad, c, e);
+    filtering_apply<N>(x, e);
+  }
+  double* fmS = fm + seq * (T + 1) * N;
+  double* fLS = fL + seq * (T + 1) * N * N;
+  if (c == 0) store_gauss_dense<N>(fmS, fLS, x);
+  OddFactorStage<N> st{reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * tma::CfgOdd<N>::LANE, fmS, fLS,
+                       k0 + 1, k1, 0};
+  double ell = 0.0;
+  SElem<N> sacc;
+  sacc.set_identity();
+#pragma unroll 1
+  for (long long k = k0; k < k1; ++k) {
+    const auto p = src.at(seq, k);
+    SElem<N> se;
+    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
+    st.template put<true>(k + 1, x);
+    if (SMOOTH) {
+      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
+      if (k == k0) sacc = se;
+      else sacc = smoothing_combine<N>(se, sacc);
+    }
+  }
+  if (ell_part) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
+    if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
+  }
+  if (SMOOTH) {
+    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
+    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+    soa_store(chunk_suf, seq, Ppad, c, excl);
+    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+  }
+  tma::bulk_wait<0>();
+}
+
 // =========================================================================================
 // Time-shard carries (multi-GPU): fold the all-gathered shard totals of the ranks before
 // (filter) / after (smoother) this one into the carry-in state.  One thread per sequence.

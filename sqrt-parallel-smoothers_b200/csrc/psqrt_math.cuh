@@ -146,12 +146,16 @@ PSQ_HD void house_rows(double (&M)[R][C]) {
       if (k + 1 < kend) sigma2 = fma(M[j][k + 1], M[j][k + 1], sigma2);
     }
     sigma += sigma2;
-    const bool live = sigma != 0.0;
+    // Branch-free on purpose: a branch around the rsqrt / rcp chain stops the scheduler from
+    // overlapping it with the independent dot products below.  Only an all-zero row needs H = I
+    // (mask = 0, like dlarfg's tau = 0); a zero tail with alpha != 0 just flips the sign of column j.
     const double q = fma(alpha, alpha, sigma);
-    const double norm = live ? q * rsqrt_nr(q) : fabs(alpha);
-    const double beta = live ? -copysign(norm, alpha) : alpha;
+    const double mask = (q != 0.0) ? 1.0 : 0.0;
+    const double qs = (q != 0.0) ? q : 1.0;
+    const double norm = qs * rsqrt_nr(qs);
+    const double beta = -copysign(norm, alpha) * mask;
     const double v0 = alpha - beta;  // = alpha + sign(alpha) * norm : no cancellation
-    const double s = live ? rcp_nr(fma(fabs(alpha), norm, q)) : 0.0;  // 1 / (norm (norm + |alpha|))
+    const double s = rcp_nr(fma(fabs(alpha), norm, qs)) * mask;  // 1 / (norm (norm + |alpha|))
     // the tail dot products do not depend on the norm: issued first so they overlap the
     // rsqrt / rcp dependency chain; v0 and s enter last
     double dots[(R - 1 > 0) ? R - 1 : 1];
@@ -183,12 +187,13 @@ PSQ_HD void tria_append(LAcc&& Lij, double (&W)[N][K]) {
     double sigma = 0.0;
     PSQ_UNROLL
     for (int k = 0; k < K; ++k) sigma = fma(W[j][k], W[j][k], sigma);
-    const bool live = sigma != 0.0;
-    const double q = fma(alpha, alpha, sigma);
-    const double norm = live ? q * rsqrt_nr(q) : fabs(alpha);
-    const double beta = live ? -copysign(norm, alpha) : alpha;
+    const double q = fma(alpha, alpha, sigma);  // branch-free, see house_rows
+    const double mask = (q != 0.0) ? 1.0 : 0.0;
+    const double qs = (q != 0.0) ? q : 1.0;
+    const double norm = qs * rsqrt_nr(qs);
+    const double beta = -copysign(norm, alpha) * mask;
     const double v0 = alpha - beta;
-    const double s = live ? rcp_nr(fma(fabs(alpha), norm, q)) : 0.0;
+    const double s = rcp_nr(fma(fabs(alpha), norm, qs)) * mask;
     PSQ_UNROLL
     for (int i = j + 1; i < N; ++i) {
       double d = 0.0;  // dot product first (independent of the norm), v0 and s last
@@ -449,7 +454,7 @@ PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
   build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
   double inv2[NY], rr[NY];
   psi11_inv_diag<N, NY>(M2, inv2);
-  double quad = 0.0, logdet = 0.0;
+  double quad = 0.0, detS = 1.0;
   PSQ_UNROLL
   for (int a = 0; a < NY; ++a) {
     double r = p.fy(a) - p.fc(a);
@@ -459,8 +464,9 @@ PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
     for (int q = 0; q < a; ++q) r = fma(-M2[a][q], rr[q], r);
     rr[a] = r * inv2[a];
     quad = fma(rr[a], rr[a], quad);
-    logdet += log(fabs(M2[a][a]));
+    detS *= M2[a][a];
   }
+  const double logdet = log(fabs(detS));  // sum_a log|Psi11_aa| with one log (NY <= 4 factors of O(1) size)
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
     double mi = mp[i];

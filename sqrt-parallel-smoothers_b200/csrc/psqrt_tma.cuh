@@ -86,5 +86,17 @@ struct Cfg {
   static constexpr size_t smem_bytes(int threads) { return (size_t)threads * LANE * sizeof(double); }
 };
 
+// Odd N: a record (8 N^2 bytes) is not a multiple of 16 bytes, but a PAIR of consecutive records that
+// starts at an even trajectory index is (16 N^2 bytes, 16-byte aligned).  The factor stream is staged
+// in such pairs; the N-double means and unpaired records at chunk ends are written directly.
+template <int N>
+struct CfgOdd {
+  static constexpr int NBUF = 2;
+  static constexpr int PAIR = 2 * N * N;
+  static constexpr int RAW = NBUF * PAIR;
+  static constexpr int LANE = (RAW / 2) % 2 == 1 ? RAW : RAW + 2;
+  static constexpr size_t smem_bytes(int threads) { return (size_t)threads * LANE * sizeof(double); }
+};
+
 }  // namespace tma
 }  // namespace psq
