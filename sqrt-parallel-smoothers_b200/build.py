@@ -19,7 +19,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "build")
+BUILD = os.environ.get("PSQRT_BUILD_DIR", os.path.join(HERE, "build"))   # tuning builds: use a separate directory
 OUT = os.path.join(HERE, "psqrt", "libpsqrt.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 

@@ -65,12 +65,13 @@ int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_
 // Workspace carving (doubles).  One layout serves the fused pass, the staged calls and the
 // element scans, so a workspace sized for the op can be reused across stages.
 struct Ws {
-  double *chunk_pref, *warp_tot, *group_f, *ftotal, *chunk_suf, *warp_stot, *group_s, *stotal, *ell_part, *ell_tmp;
-  double* selems;  // [B][K][nf_smoother][Ppad] smoothing elements handed from the forward to the backward sweep
+  double *chunk_own, *chunk_pref, *warp_tot, *group_f, *ftotal, *chunk_suf, *warp_stot, *group_s, *stotal, *ell_part,
+      *ell_tmp;
+  double* fpack;  // [B][K][nf_state][Ppad] packed filtered states handed from the forward to the backward sweep
   unsigned int *counter_f, *counter_s;
   size_t doubles;
 };
-Ws carve(void* base, const psqrt_plan& p, int64_t B) {
+Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B) {
   Ws w;
   double* d = (double*)base;
   size_t off = 0;
@@ -79,6 +80,7 @@ Ws carve(void* base, const psqrt_plan& p, int64_t B) {
     off += (n + 1) & ~(size_t)1;  // keep 16-byte alignment
     return r;
   };
+  w.chunk_own = take((size_t)B * p.nf_filter * p.n_chunks_pad);
   w.chunk_pref = take((size_t)B * p.nf_filter * p.n_chunks_pad);
   const size_t G = (size_t)(p.n_warps + 31) / 32;
   w.warp_tot = take((size_t)B * p.nf_filter * p.n_warps);
@@ -92,7 +94,7 @@ Ws carve(void* base, const psqrt_plan& p, int64_t B) {
   w.ell_tmp = take((size_t)B);
   w.counter_f = (unsigned int*)take((size_t)B);   // one 8-byte slot per sequence, used as uint32
   w.counter_s = (unsigned int*)take((size_t)B);
-  w.selems = take((size_t)B * (size_t)p.chunk_len * (size_t)p.nf_smoother * (size_t)p.n_chunks_pad);
+  w.fpack = take((size_t)B * (size_t)p.chunk_len * (size_t)nf_state * (size_t)p.n_chunks_pad);
   w.doubles = off;
   return w;
 }
@@ -146,7 +148,7 @@ int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws,
   if (B > 65535) return PSQRT_EINVAL;
   int rc = make_plan(c.ln, T, B, chunk_len, &c.plan);
   if (rc) return rc;
-  c.ws = carve(ws, c.plan, B);
+  c.ws = carve(ws, c.plan, c.ln->nf_state, B);
   if (!ws || ws_bytes < c.ws.doubles * sizeof(double)) return PSQRT_EWORKSPACE;
   return PSQRT_OK;
 }
@@ -189,7 +191,7 @@ size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, i
   const LaunchN* ln = table_for(nx);
   psqrt_plan p;
   if (!ln || make_plan(ln, T, batch, chunk_len, &p)) return 0;
-  return carve(nullptr, p, batch).doubles * sizeof(double);
+  return carve(nullptr, p, ln->nf_state, batch).doubles * sizeof(double);
 }
 
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
@@ -201,8 +203,8 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
   HostModel hmv;
-  c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref, c.ws.warp_tot,
-                       c.ws.counter_f, st);
+  c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_own,
+                       c.ws.chunk_pref, c.ws.warp_tot, c.ws.counter_f, st);
   c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, ftotal ? ftotal : c.ws.ftotal,
                    st);
   return check_launch();
@@ -228,9 +230,9 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   SSMArgs a = make_args(ssm, y, ny, T);
   const int smooth = stotal != nullptr;
   HostModel hmv;
-  c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, c.ws.chunk_pref,
-                      c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
-                      ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.selems, st);
+  c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m,
+                      carry_L, c.ws.chunk_own, c.ws.chunk_pref, c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf,
+                      c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.fpack, st);
   if (smooth) {
     c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, stotal,
                      ell ? c.ws.ell_part : nullptr, ell, st);
@@ -254,14 +256,16 @@ int psqrt_carry_smoother(const double* totals, int rank, int n_ranks, int64_t ba
 int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
                          double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
-  (void)ssm; (void)fm; (void)fL;  // the smoothing elements were stored in the workspace by psqrt_filter_apply
-  if (!carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
+  (void)fm; (void)fL;  // psqrt_filter_apply left the packed filtered states in the workspace
+  if (!ssm_ok(ssm, false) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
-  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L, nx, (long long)nx * nx,
-                     c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.selems, sm, sL, write_terminal,
-                     (cudaStream_t)stream);
+  SSMArgs a = make_args(ssm, nullptr, 0, T);
+  HostModel hmv;
+  c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L,
+                     nx, (long long)nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL,
+                     write_terminal, (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -279,9 +283,12 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
                           ws_bytes, stream);
   if (rc || !smooth) return rc;
   // terminal carry = filtered state at index T of every sequence
-  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx, fL + (size_t)T * nx * nx,
-                     (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot,
-                     c.ws.group_s, c.ws.selems, sm, sL, 1, (cudaStream_t)stream);
+  SSMArgs a = make_args(ssm, nullptr, 0, T);
+  HostModel hmv;
+  c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
+                     fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,
+                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL, 1,
+                     (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -294,13 +301,14 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
   HostModel hmv;
-  c.ln->smooth_reduce(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL, c.ws.chunk_suf, c.ws.warp_stot,
-                      c.ws.counter_s, c.ws.selems, st);
+  c.ln->smooth_reduce(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL,
+                      c.ws.chunk_suf, c.ws.warp_stot, c.ws.counter_s, c.ws.fpack, st);
   c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
                    st);
-  c.ln->smooth_apply(T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm + (size_t)T * nx, fL + (size_t)T * nx * nx,
-                     (long long)(T + 1) * nx, (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot,
-                     c.ws.group_s, c.ws.selems, sm, sL, 1, st);
+  c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
+                     fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,
+                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL, 1,
+                     st);
   return check_launch();
 }
 

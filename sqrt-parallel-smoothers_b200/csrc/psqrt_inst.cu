@@ -44,64 +44,70 @@ SrcVal<N, NY> make_src_val(const HostModel& h, const SSMArgs& a) {
   return s;
 }
 
+template <int NN>
+SrcValT<NN> make_src_valT(const HostModel& h) {
+  SrcValT<NN> s;
+  for (int i = 0; i < NN * NN; ++i) { s.m.F[i] = h.F[i]; s.m.Q[i] = h.Q[i]; }
+  for (int i = 0; i < NN; ++i) s.m.bq[i] = h.bq[i];
+  return s;
+}
+
 inline dim3 sweep_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kBlock), (unsigned)B, 1); }
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// How a sweep writes its trajectory (psqrt_kernels.cuh, WarpOut): 16-byte words when the records are
+// multiples of 16 bytes (even N) and the bases are 16-byte aligned, 8-byte words otherwise.
+template <int NN>
+bool vec2_ok(const void* m, const void* L) {
+  return NN % 2 == 0 && aligned16(m) && aligned16(L);
+}
+template <class KERN, class... Args>
+void launch_sweep(KERN kern, size_t smem, long long Ppad, long long B, cudaStream_t st, Args... args) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(args...);
+}
 
 template <int NY>
 struct NYImpl {
   static void filter_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
-                            double* chunk_pref, double* warp_tot, unsigned int* counter, cudaStream_t st) {
+                            double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter,
+                            cudaStream_t st) {
+    const size_t ysmem = LaneRing<NY, kYDepth>::smem_bytes(kBlock);
     if constexpr (kByValue) {
       if (hm) {
-        k_filter_reduce<N, NY, SrcVal<N, NY>><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(make_src_val<NY>(*hm, a), T, K,
-                                                                                     Ppad, chunk_pref, warp_tot, counter);
+        launch_sweep(k_filter_reduce<N, NY, SrcVal<N, NY>>, ysmem, Ppad, B, st, make_src_val<NY>(*hm, a), T, K, Ppad,
+                     chunk_own, chunk_pref, warp_tot, counter);
         return;
       }
     }
-    {
-      k_filter_reduce<N, NY, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, chunk_pref, warp_tot,
-                                                                            counter);
-    }
+    launch_sweep(k_filter_reduce<N, NY, SrcPtr>, ysmem, Ppad, B, st, SrcPtr{a}, T, K, Ppad, chunk_own, chunk_pref,
+                 warp_tot, counter);
   }
-  static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
   template <bool SMOOTH, class SRC>
   static void filter_apply_t(const SRC& src, long long T, int K, long long Ppad, long long B, const double* cm,
-                             const double* cL, const double* chunk_pref, const double* warp_pref,
-                             const double* group_pref, double* fm, double* fL, double* chunk_suf, double* warp_stot,
-                             double* ell_part, unsigned int* counter_s, double* selems, cudaStream_t st) {
-    if constexpr (tma::Cfg<N>::S > 0) {
-      if (aligned16(fm) && aligned16(fL)) {   // staged stores (TMA bulk copies)
-        const size_t smem = tma::Cfg<N>::smem_bytes(kBlock);
-        auto kern = k_filter_apply_tma<N, NY, SMOOTH, SRC>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm,
-                                                       fL, chunk_suf, warp_stot, ell_part, counter_s, selems);
-        return;
-      }
+                             const double* cL, const double* chunk_own, const double* chunk_pref,
+                             const double* warp_pref, const double* group_pref, double* fm, double* fL,
+                             double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
+                             double* fpack, cudaStream_t st) {
+#define PSQ_K3(OUT)                                                                                                  \
+  launch_sweep(k_filter_apply<N, NY, SMOOTH, SRC, OUT>, OUT::smem_bytes(kBlock) + LaneRing<NY, kYDepth>::smem_bytes(kBlock), Ppad, B, st, src, T, K, Ppad, cm, \
+               cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s, \
+               fpack)
+    if constexpr (N % 2 == 0) {
+      if (vec2_ok<N>(fm, fL)) { using O = WarpOut<N, 2>; PSQ_K3(O); return; }
     }
-    if constexpr (N % 2 == 1) {
-      // pair-staged factor stream: pairs start at even indices, so every sequence must start 16-byte aligned
-      if (aligned16(fL) && (B == 1 || (T + 1) % 2 == 0)) {
-        const size_t smem = tma::CfgOdd<N>::smem_bytes(kBlock);
-        auto kern = k_filter_apply_tma_odd<N, NY, SMOOTH, SRC>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm,
-                                                       fL, chunk_suf, warp_stot, ell_part, counter_s, selems);
-        return;
-      }
-    }
-    k_filter_apply<N, NY, SMOOTH, SRC><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(
-        src, T, K, Ppad, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s,
-        selems);
+    { using O = WarpOut<N, 1>; PSQ_K3(O); }
+#undef PSQ_K3
   }
   static void filter_apply(int smooth, const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad,
-                           long long B, const double* cm, const double* cL, const double* chunk_pref,
-                           const double* warp_pref, const double* group_pref, double* fm, double* fL,
-                           double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
-                           double* selems, cudaStream_t st) {
+                           long long B, const double* cm, const double* cL, const double* chunk_own,
+                           const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
+                           double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
+                           unsigned int* counter_s, double* fpack, cudaStream_t st) {
 #define PSQ_FA(SM, SRCV)                                                                                             \
-  filter_apply_t<SM>(SRCV, T, K, Ppad, B, cm, cL, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot,  \
-                     ell_part, counter_s, selems, st)
+  filter_apply_t<SM>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, \
+                     warp_stot, ell_part, counter_s, fpack, st)
     if constexpr (kByValue) {
       if (hm) {
         const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
@@ -157,44 +163,38 @@ void mid_smooth(double* items, long long M, long long B, double* groups, unsigne
 }
 void smooth_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                    const double* fm, const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter,
-                   double* selems, cudaStream_t st) {
+                   double* fpack, cudaStream_t st) {
   (void)hm;  // the standalone smoother is not a hot path: pointer model only
   k_smooth_reduce<N, SrcPtr><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(SrcPtr{a}, T, K, Ppad, fm, fL, chunk_suf,
-                                                                      warp_stot, counter, selems);
+                                                                      warp_stot, counter, fpack);
 }
-template <int NN>
-void smooth_apply_t(long long T, int K, long long Ppad, long long B, const double* cm, const double* cL,
-                    long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
-                    const double* group_suf, const double* selems, double* sm, double* sL, int write_terminal,
+template <class SRC>
+void smooth_apply_t(const SRC& src, long long T, int K, long long Ppad, long long B, const double* cm,
+                    const double* cL, long long cms, long long cLs, const double* chunk_suf, const double* warp_suf,
+                    const double* group_suf, const double* fpack, double* sm, double* sL, int write_terminal,
                     cudaStream_t st) {
-  if constexpr (tma::Cfg<NN>::S > 0) {
-    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (al(sm) && al(sL)) {   // staged loads + stores (TMA bulk copies)
-      const size_t smem = tma::Cfg<NN>::smem_bytes(kBlock);
-      auto kern = k_smooth_apply_tma<NN>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
-                                                     selems, sm, sL, write_terminal);
-      return;
-    }
+#define PSQ_K5(OUT)                                                                                                  \
+  launch_sweep(k_smooth_apply<N, SRC, OUT>, OUT::smem_bytes(kBlock) + LaneRing<N + Gauss<N>::TRI, kXDepth>::smem_bytes(kBlock), Ppad, B, st, src, T, K, Ppad, cm, cL, cms, cLs, \
+               chunk_suf, warp_suf, group_suf, fpack, sm, sL, write_terminal)
+  if constexpr (N % 2 == 0) {
+    if (vec2_ok<N>(sm, sL)) { using O = WarpOut<N, 2>; PSQ_K5(O); return; }
   }
-  if constexpr (NN % 2 == 1) {
-    if ((reinterpret_cast<uintptr_t>(sL) & 15u) == 0 && (B == 1 || (T + 1) % 2 == 0)) {
-      const size_t smem = tma::CfgOdd<NN>::smem_bytes(kBlock);
-      auto kern = k_smooth_apply_tma_odd<NN>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
-                                                     selems, sm, sL, write_terminal);
-      return;
-    }
-  }
-  k_smooth_apply<NN><<<sweep_grid(Ppad, B), kBlock, 0, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf,
-                                                            selems, sm, sL, write_terminal);
+  { using O = WarpOut<N, 1>; PSQ_K5(O); }
+#undef PSQ_K5
 }
-void smooth_apply(long long T, int K, long long Ppad, long long B, const double* cm, const double* cL, long long cms,
-                  long long cLs, const double* chunk_suf, const double* warp_suf, const double* group_suf,
-                  const double* selems, double* sm, double* sL, int write_terminal, cudaStream_t st) {
-  smooth_apply_t<N>(T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, selems, sm, sL, write_terminal, st);
+void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
+                  const double* cm, const double* cL, long long cms, long long cLs, const double* chunk_suf,
+                  const double* warp_suf, const double* group_suf, const double* fpack, double* sm, double* sL,
+                  int write_terminal, cudaStream_t st) {
+  if constexpr (kByValue) {
+    if (hm) {
+      smooth_apply_t(make_src_valT<N>(*hm), T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm,
+                     sL, write_terminal, st);
+      return;
+    }
+  }
+  smooth_apply_t(SrcPtr{a}, T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm, sL,
+                 write_terminal, st);
 }
 void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                   double* cL, cudaStream_t st) {
@@ -250,6 +250,7 @@ void chol_update(double* L, const double* V, int k, double alpha, long long batc
 const LaunchN kTable = {N,
                         FElem<N>::NF,
                         SElem<N>::NF,
+                        N + Gauss<N>::TRI,
                         &for_ny,
                         &mid_filter,
                         &mid_smooth,

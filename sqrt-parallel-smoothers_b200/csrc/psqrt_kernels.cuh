@@ -21,12 +21,14 @@
 #include <stdint.h>
 
 #include "psqrt_math.cuh"
-#include "psqrt_tma.cuh"
+#include "psqrt_async.cuh"
 
 namespace psq {
 
 constexpr int kBlock = 128;      // threads per CTA in the sweeps (4 warps)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kYDepth = 4;       // observations are fetched this many steps ahead (psqrt_async.cuh)
+constexpr int kXDepth = 2;       // packed filtered states of the backward sweep likewise
 // minimum resident CTAs per SM requested from ptxas for the three sweeps (register cap =
 // 65536 / (128 * MINB)); tuned on B200, see DESIGN.md section 5
 #ifndef PSQ_MINB_K1
@@ -65,6 +67,7 @@ __device__ __forceinline__ StepPtrs step_ptrs(const SSMArgs& a, long long seq, l
 struct SrcPtr {
   SSMArgs a;
   __device__ __forceinline__ StepPtrs at(long long seq, long long k) const { return step_ptrs(a, seq, k); }
+  __device__ __forceinline__ const double* yp(long long seq, long long k) const { return a.y + seq * a.sy + k * a.ty; }
 };
 template <int N, int NY>
 struct SrcVal {
@@ -74,6 +77,12 @@ struct SrcVal {
   __device__ __forceinline__ StepVals<N, NY> at(long long seq, long long k) const {
     return StepVals<N, NY>{m, y ? y + seq * sy + k * ty : nullptr};
   }
+  __device__ __forceinline__ const double* yp(long long seq, long long k) const { return y + seq * sy + k * ty; }
+};
+template <int N>
+struct SrcValT {  // transition model only (backward sweep)
+  ModelValsT<N> m;
+  __device__ __forceinline__ StepValsT<N> at(long long, long long) const { return StepValsT<N>{m}; }
 };
 
 // ---- element traits: combine(acc, x) with acc = everything earlier in SCAN order ------------
@@ -157,33 +166,119 @@ __device__ __forceinline__ void store_gauss_dense(double* m, double* L, const Ga
   }
 }
 
-// Smoothing elements travel from the forward sweep (K3) to the backward sweep (K5) through a scratch
-// array, so K5 only applies them instead of re-deriving each one from the filtered state with another
-// 2N x 2N triangularisation.  Layout [B][K][NF][Ppad]: step j of chunk c keeps field f at
-// ((j * NF + f) * Ppad + c), i.e. the 32 lanes of a warp (consecutive chunks, same j) touch 32
-// consecutive doubles -- fully coalesced plain loads / stores, no staging needed.
+// The filtered states travel from the forward sweep (K3) to the backward sweep (K5) a second time in a
+// packed, warp-coalesced scratch array next to the API trajectory: K5 then needs no staging for its
+// input.  Layout [B][K][NP][Ppad], NP = N + N(N+1)/2 (mean + lower triangle): slot j of chunk c (the
+// filtered state at trajectory index c K + j, i.e. BEFORE step c K + j) keeps field f at
+// ((j * NP + f) * Ppad + c), so the 32 lanes of a warp (consecutive chunks, same j) touch 32 consecutive
+// doubles -- fully coalesced plain loads / stores.
 template <int N>
-__device__ __forceinline__ void selem_store(double* selems, long long seq, int K, long long Ppad, long long c, int j,
-                                            const SElem<N>& e) {
-  double* p = selems + ((seq * K + j) * SElem<N>::NF) * Ppad + c;
+__device__ __forceinline__ void fpack_store(double* fpack, long long seq, int K, long long Ppad, long long c, int j,
+                                            const Gauss<N>& x) {
+  constexpr int NP = N + Gauss<N>::TRI;
+  double* p = fpack + ((seq * K + j) * NP) * Ppad + c;
 #pragma unroll
-  for (int f = 0; f < SElem<N>::NF; ++f) p[f * Ppad] = e.v[f];
-}
-template <int N>
-__device__ __forceinline__ void selem_load(const double* selems, long long seq, int K, long long Ppad, long long c,
-                                           int j, SElem<N>& e) {
-  const double* p = selems + ((seq * K + j) * SElem<N>::NF) * Ppad + c;
+  for (int f = 0; f < N; ++f) p[f * Ppad] = x.m[f];
 #pragma unroll
-  for (int f = 0; f < SElem<N>::NF; ++f) e.v[f] = __ldg(p + f * Ppad);
+  for (int f = 0; f < Gauss<N>::TRI; ++f) p[(N + f) * Ppad] = x.L[f];
 }
+// The observation of the step being processed comes out of the prefetch ring (psqrt_async.cuh); this
+// adaptor hands it to the algebra in place of the pointer.
+template <class P, int NY>
+struct WithY {
+  const P& p;
+  const double (&yv)[NY];
+  template <int N_> __device__ __forceinline__ double fF(int i, int j) const { return p.template fF<N_>(i, j); }
+  template <int N_> __device__ __forceinline__ double fQ(int i, int j) const { return p.template fQ<N_>(i, j); }
+  __device__ __forceinline__ double fb(int i) const { return p.fb(i); }
+  template <int N_> __device__ __forceinline__ double fH(int a, int k) const { return p.template fH<N_>(a, k); }
+  template <int NY_> __device__ __forceinline__ double fR(int a, int q) const { return p.template fR<NY_>(a, q); }
+  __device__ __forceinline__ double fc(int a) const { return p.fc(a); }
+  __device__ __forceinline__ double fy(int a) const { return yv[a]; }
+};
+// =========================================================================================
+// WarpOut: how a sweep writes the API trajectories (mean [*, N], factor [*, N, N]).
+// Every lane owns a run of consecutive records, K x REC x 8 bytes away from its neighbour's: written
+// directly, one warp-wide store touches 32 different cache lines.  Instead each lane parks the record of
+// the current step in the warp's shared-memory tile ([32][RECP], padded against bank conflicts) and the
+// warp then copies the tile out together: consecutive lanes write consecutive 16-byte (VEC = 2; even N,
+// 16-byte aligned bases) or 8-byte (VEC = 1) words of one record, so each store instruction covers whole
+// 32-byte sectors -- for N = 4 a factor record is exactly one 128-byte line.
+// (Round-1 history: per-lane TMA bulk copies did this job before.  cp.async.bulk is a warp-uniform
+// instruction -- SASS UBLKCP behind a 12-instruction loop over the 32 lanes -- and cost ~380 issue slots
+// per step; see DESIGN.md.)
+// All 32 lanes of a warp must call put() in lockstep; `active` says whether this lane has a record.
+// =========================================================================================
+template <int N, int VEC>
+struct WarpOut {
+  static constexpr int REC = N + N * N;
+  // lane stride in doubles: odd number of VEC-words
+  static constexpr int RECP = (VEC == 2) ? (((REC / 2) % 2 == 1) ? REC : REC + 2) : ((REC % 2 == 1) ? REC : REC + 1);
+  static constexpr size_t smem_bytes(int threads) { return (size_t)threads * RECP * sizeof(double); }
+  double* tile;   // this warp's [32][RECP]
+  double *gm, *gL;
+  long long c0;   // first chunk of the warp
+  long long T;
+  int K, voff, lane;
+  // lane t writes trajectory index (c0 + t) K + j at step j, provided (c0 + t) K + j + voff < T
+  __device__ __forceinline__ WarpOut(unsigned char* smem, double* m, double* L, long long c, int K_, long long T_, int voff_)
+      : tile(reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x & ~31) * RECP), gm(m), gL(L),
+        c0(c - (threadIdx.x & 31)), T(T_), K(K_), voff(voff_), lane(threadIdx.x & 31) {}
+
+  template <int W, int PER>   // W doubles per word, PER words per record; src offset in the tile record, dst array
+  __device__ __forceinline__ void copy_part(int j, int src_off, double* g) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {   // 32 * PER words in the tile, 32 per iteration
+      const int e = i * 32 + lane;
+      const int t = e / PER, o = e - t * PER;
+      const long long k0 = (c0 + t) * K;
+      if (k0 + j + voff < T) {   // lane t has a record at this step
+        const double* sp = tile + t * RECP + src_off + o * W;
+        double* gp = g + (k0 + j) * (long long)(PER * W) + o * W;
+        if (W == 2) *reinterpret_cast<double2*>(gp) = *reinterpret_cast<const double2*>(sp);
+        else *gp = *sp;
+      }
+    }
+  }
+  __device__ __forceinline__ void put(int j, bool active, const Gauss<N>& x) {
+    if (active) {
+      double* r = tile + lane * RECP;
+      if (VEC == 2) {
+#pragma unroll
+        for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(r + i) = make_double2(x.m[i], x.m[i + 1]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+#pragma unroll
+          for (int q = 0; q < N; q += 2) {
+            const double a = (q <= i) ? x.Lc(i, q) : 0.0;
+            const double b = (q + 1 <= i) ? x.Lc(i, q + 1) : 0.0;
+            *reinterpret_cast<double2*>(r + N + i * N + q) = make_double2(a, b);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = x.m[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+          for (int q = 0; q < N; ++q) r[N + i * N + q] = (q <= i) ? x.Lc(i, q) : 0.0;
+      }
+    }
+    __syncwarp();
+    copy_part<VEC, N / VEC>(j, 0, gm);
+    copy_part<VEC, N * N / VEC>(j, N, gL);
+    __syncwarp();
+  }
+};
 
 // =========================================================================================
 // K1
 // =========================================================================================
 template <int N, int NY, class SRC>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K1)
-k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, double* __restrict__ chunk_pref,
-                double* __restrict__ warp_tot, unsigned int* __restrict__ counter) {
+k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, double* __restrict__ chunk_own,
+                double* __restrict__ chunk_pref, double* __restrict__ warp_tot, unsigned int* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -192,16 +287,29 @@ k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
   acc.set_identity();
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
+  // observations arrive through a per-lane cp.async ring, kYDepth steps ahead of their use
+  LaneRing<NY, kYDepth> yring(smem_raw);
+#pragma unroll
+  for (int d = 0; d < kYDepth; ++d) yring.issue(d, k0 + d < k1, src.yp(seq, k0 + d), 1);
+  int slot = 0;
 #pragma unroll 1
   for (long long k = k0; k < k1; ++k) {
+    double ycur[NY];
+    yring.wait_oldest();
+#pragma unroll
+    for (int a = 0; a < NY; ++a) ycur[a] = yring.get(slot, a);
+    yring.issue(slot, k + kYDepth < k1, src.yp(seq, k + kYDepth), 1);
+    slot = (slot + 1 == kYDepth) ? 0 : slot + 1;
     const auto p = src.at(seq, k);
-    filter_reduce_step<N, NY>(acc, p);
+    filter_reduce_step<N, NY>(acc, WithY<decltype(p), NY>{p, ycur});
   }
+  soa_store(chunk_own, seq, Ppad, c, acc);  // K3 derives the chunk's smoothing total from it
   FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(acc, lane);
   FElem<N> excl = warp_exclusive_from_inclusive<FElem<N>, false>(incl, lane);
   soa_store(chunk_pref, seq, Ppad, c, excl);
   if (lane == 31) soa_store(warp_tot, seq, Ppad / 32, c / 32, incl);
 }
+
 
 // =========================================================================================
 // K2 / K4: exclusive scan of the M warp totals of one sequence, two levels in one launch.
@@ -282,15 +390,16 @@ k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ groups,
 // =========================================================================================
 // K3
 // =========================================================================================
-template <int N, int NY, bool SMOOTH, class SRC>
+template <int N, int NY, bool SMOOTH, class SRC, class OUT>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
 k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // [B][N], [B][N][N] lower
-               const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
-               const double* __restrict__ group_pref,
+               const double* __restrict__ chunk_own, const double* __restrict__ chunk_pref,
+               const double* __restrict__ warp_pref, const double* __restrict__ group_pref,
                double* __restrict__ fm, double* __restrict__ fL,  // [B][T+1][N], [B][T+1][N][N]; index k+1 written
                double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
-               unsigned int* __restrict__ counter, double* __restrict__ selems) {
+               unsigned int* __restrict__ counter, double* __restrict__ fpack) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -299,6 +408,9 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   const long long k1 = (k0 + K < T) ? k0 + K : T;
 
   if (SMOOTH && c == 0) counter[seq] = 0u;
+  LaneRing<NY, kYDepth> yring(smem_raw + OUT::smem_bytes(kBlock));
+#pragma unroll
+  for (int d = 0; d < kYDepth; ++d) yring.issue(d, k0 + d < k1, src.yp(seq, k0 + d), 1);
   Gauss<N> x;
   load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
   {
@@ -313,19 +425,55 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   double* fmS = fm + seq * (T + 1) * N;
   double* fLS = fL + seq * (T + 1) * N * N;
   if (c == 0) store_gauss_dense<N>(fmS, fLS, x);  // trajectory index 0 = carry-in state
+  if (SMOOTH) {
+    // the chunk's smoothing total from its filtering summary and the state it starts from, then the
+    // suffix scan across the warp: nothing of the smoother stays live in the step loop below
+    SElem<N> sacc;
+    sacc.set_identity();
+    if (k0 < k1) {
+      FElem<N> e;
+      soa_load(chunk_own, seq, Ppad, c, e);
+      chunk_smoothing_total<N>(x, e, sacc);
+    }
+    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
+    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
+    soa_store(chunk_suf, seq, Ppad, c, excl);
+    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+  }
+  // The step loop runs K + 1 times in every lane of a warp that has any work (the cooperative writes
+  // need the whole warp); lanes past the end of the sequence idle through it.  Inside the chunk the
+  // recursion carries a dense square-root factor and iteration j advances it by step k0 + j WHILE it
+  // triangularises and writes out the state at index k0 + j (psq::kalman_step_dense).
+  const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
+  OUT out(smem_raw, fmS, fLS, c, K, T, -1);
   double ell = 0.0;
-  SElem<N> sacc;
-  sacc.set_identity();
+  int slot = 0;
+  if ((c - lane) * K < T) {
+    GaussD<N> xd;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      xd.m[i] = x.m[i];
+#pragma unroll
+      for (int q = 0; q < N; ++q) xd.Y[i][q] = (q <= i) ? x.Lc(i, q) : 0.0;
+    }
 #pragma unroll 1
-  for (long long k = k0; k < k1; ++k) {
-    const auto p = src.at(seq, k);
-    SElem<N> se;
-    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
-    store_gauss_dense<N>(fmS + (k + 1) * N, fLS + (k + 1) * N * N, x);
-    if (SMOOTH) {
-      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
-      if (k == k0) sacc = se;
-      else sacc = smoothing_combine<N>(se, sacc);  // se is the later side
+    for (int j = 0; j <= K; ++j) {
+      if (j < len) {
+        const long long k = k0 + j;
+        double ycur[NY];
+        yring.wait_oldest();
+#pragma unroll
+        for (int a = 0; a < NY; ++a) ycur[a] = yring.get(slot, a);
+        yring.issue(slot, j + kYDepth < len, src.yp(seq, k + kYDepth), 1);
+        slot = (slot + 1 == kYDepth) ? 0 : slot + 1;
+        const auto p = src.at(seq, k);
+        if (ell_part) ell += kalman_step_dense<N, NY, true>(xd, WithY<decltype(p), NY>{p, ycur}, x);
+        else kalman_step_dense<N, NY, false>(xd, WithY<decltype(p), NY>{p, ycur}, x);
+        if (SMOOTH) fpack_store<N>(fpack, seq, K, Ppad, c, j, x);  // filtered state at index k
+      } else if (j == len) {
+        gaussd_tri<N>(xd, x);
+      }
+      if (j > 0) out.put(j, j <= len, x);  // trajectory index k0 + j
     }
   }
   if (ell_part) {
@@ -333,20 +481,15 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
     for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
     if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
   }
-  if (SMOOTH) {
-    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
-    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
-    soa_store(chunk_suf, seq, Ppad, c, excl);
-    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
-  }
 }
 
-// Standalone smoothing reduce (smoothing(...) called on an existing filter trajectory).
+// Standalone smoothing reduce (smoothing(...) called on an existing filter trajectory): no filtering
+// summaries exist, so the chunk totals are the ordered combine of the per-step elements.
 template <int N, class SRC>
 __global__ void __launch_bounds__(kBlock)
 k_smooth_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, const double* __restrict__ fm,
                 const double* __restrict__ fL, double* __restrict__ chunk_suf, double* __restrict__ warp_stot,
-                unsigned int* __restrict__ counter, double* __restrict__ selems) {
+                unsigned int* __restrict__ counter, double* __restrict__ fpack) {
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -363,9 +506,9 @@ k_smooth_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
     const auto p = src.at(seq, k);
     Gauss<N> xf;
     load_gauss_dense<N>(fmS + k * N, fLS + k * N * N, xf);
+    fpack_store<N>(fpack, seq, K, Ppad, c, (int)(k - k0), xf);
     SElem<N> se;
     smoothing_element<N>(xf, p, se);
-    selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
     sacc = (k == k0) ? se : smoothing_combine<N>(se, sacc);
   }
   SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
@@ -377,26 +520,34 @@ k_smooth_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
 // =========================================================================================
 // K5
 // =========================================================================================
-template <int N>
+template <int N, class SRC, class OUT>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
-k_smooth_apply(long long T, int K, long long Ppad,
+k_smooth_apply(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // smoothed state at index T
                long long carry_mstride, long long carry_Lstride,
                const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
-               const double* __restrict__ group_suf, const double* __restrict__ selems,
+               const double* __restrict__ group_suf, const double* __restrict__ fpack,
                double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const long long Mw = Ppad / 32;
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
-  if (k0 >= k1) return;  // no warp-level communication below this point
-  Gauss<N> xs;
-  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
+  if ((c - lane) * K >= T) return;  // the whole warp lies past the end of the sequence
+  const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
   double* smS = sm + seq * (T + 1) * N;
   double* sLS = sL + seq * (T + 1) * N * N;
-  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
-  {
+  constexpr int NP = N + Gauss<N>::TRI;
+  LaneRing<NP, kXDepth> xring(smem_raw + OUT::smem_bytes(kBlock));
+  const double* fp = fpack + (seq * K * NP) * Ppad + c;  // slot j of this chunk: fp + j NP Ppad, field stride Ppad
+#pragma unroll
+  for (int d = 0; d < kXDepth; ++d) xring.issue(d, len - 1 - d >= 0, fp + (long long)(len - 1 - d) * NP * Ppad, Ppad);
+  Gauss<N> xs;
+  if (len > 0) {
+    load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
+    if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
     SElem<N> e;
     soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);  // groups are in scan (reverse) order
     smoothing_apply<N>(xs, e);
@@ -405,353 +556,24 @@ k_smooth_apply(long long T, int K, long long Ppad,
     soa_load(chunk_suf, seq, Ppad, c, e);
     smoothing_apply<N>(xs, e);
   }
-  SElem<N> se;
-  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
+  OUT out(smem_raw, smS, sLS, c, K, T, 0);
+  int slot = 0;
 #pragma unroll 1
-  for (long long k = k1 - 1; k >= k0; --k) {
-    SElem<N> nxt;
-    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);  // in flight during the apply
-    smoothing_apply<N>(xs, se);
-    store_gauss_dense<N>(smS + k * N, sLS + k * N * N, xs);
-    se = nxt;
-  }
-}
-
-// =========================================================================================
-// Staged variants of K5 and K3 (even N, 16-byte aligned trajectories): records move between HBM
-// and a per-lane shared-memory slice with TMA bulk copies (psqrt_tma.cuh).
-// =========================================================================================
-template <int N>
-__device__ __forceinline__ void load_gauss_smem(const double* m, const double* L, Gauss<N>& x) {
-  static_assert(N % 2 == 0, "staged path needs even N");
+  for (int j = K - 1; j >= 0; --j) {
+    const bool active = j < len;
+    if (active) {
+      Gauss<N> xf;
+      xring.wait_oldest();
 #pragma unroll
-  for (int i = 0; i < N; i += 2) {
-    const double2 v = *reinterpret_cast<const double2*>(m + i);
-    x.m[i] = v.x;
-    x.m[i + 1] = v.y;
-  }
+      for (int f = 0; f < N; ++f) xf.m[f] = xring.get(slot, f);
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-#pragma unroll
-    for (int j = 0; j <= i; j += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(L + i * N + j);
-      x.Lc(i, j) = v.x;
-      if (j + 1 <= i) x.Lc(i, j + 1) = v.y;
+      for (int f = 0; f < Gauss<N>::TRI; ++f) xf.L[f] = xring.get(slot, N + f);
+      xring.issue(slot, j - kXDepth >= 0, fp + (long long)(j - kXDepth) * NP * Ppad, Ppad);
+      slot = (slot + 1 == kXDepth) ? 0 : slot + 1;
+      rts_step<N>(xs, xf, src.at(seq, k0 + j));
     }
+    out.put(j, active, xs);  // trajectory index k0 + j
   }
-}
-template <int N>
-__device__ __forceinline__ void store_gauss_smem(double* m, double* L, const Gauss<N>& x) {
-#pragma unroll
-  for (int i = 0; i < N; i += 2) *reinterpret_cast<double2*>(m + i) = make_double2(x.m[i], x.m[i + 1]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-#pragma unroll
-    for (int j = 0; j < N; j += 2) {
-      const double a = (j <= i) ? x.Lc(i, j) : 0.0;
-      const double b = (j + 1 <= i) ? x.Lc(i, j + 1) : 0.0;
-      *reinterpret_cast<double2*>(L + i * N + j) = make_double2(a, b);
-    }
-  }
-}
-
-template <int N>
-__global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
-k_smooth_apply_tma(long long T, int K, long long Ppad,
-                   const double* __restrict__ carry_m, const double* __restrict__ carry_L,
-                   long long carry_mstride, long long carry_Lstride,
-                   const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
-                   const double* __restrict__ group_suf, const double* __restrict__ selems,
-                   double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
-  using CF = tma::Cfg<N>;
-  constexpr int S = CF::SS, NBUF = CF::NB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* slice = reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * CF::LANE;
-
-  const long long seq = blockIdx.y;
-  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const long long Mw = Ppad / 32;
-  const long long k0 = c * K;
-  const long long k1 = (k0 + K < T) ? k0 + K : T;
-  if (k0 >= k1) return;
-  double* smS = sm + seq * (T + 1) * N;
-  double* sLS = sL + seq * (T + 1) * N * N;
-  SElem<N> se;
-  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
-
-  Gauss<N> xs;
-  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
-  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
-  {
-    SElem<N> e;
-    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);
-    smoothing_apply<N>(xs, e);
-    soa_load(warp_suf, seq, Mw, c / 32, e);
-    smoothing_apply<N>(xs, e);
-    soa_load(chunk_suf, seq, Ppad, c, e);
-    smoothing_apply<N>(xs, e);
-  }
-  // output tiles [lo, hi) of up to S records, walked from the top slot down, NBUF tiles in rotation
-  int t = 0;
-  long long hi = k1;
-#pragma unroll 1
-  for (long long k = k1 - 1; k >= k0; --k) {
-    SElem<N> nxt;
-    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);  // in flight during the apply
-    smoothing_apply<N>(xs, se);
-    const long long lo = (hi - S > k0) ? hi - S : k0;
-    double* buf = slice + (t % NBUF) * CF::BUF_DOUBLES;
-    if (k == hi - 1) {  // first write into this buffer: the store issued NBUF tiles ago must have drained it
-      if (NBUF > 1) tma::bulk_wait_read<NBUF - 1>(); else tma::bulk_wait_read<0>();
-    }
-    const int slot = (int)(k - lo);
-    store_gauss_smem<N>(buf + slot * N, buf + S * N + slot * N * N, xs);
-    if (k == lo) {
-      const unsigned cnt = (unsigned)(hi - lo);
-      tma::fence_proxy_async();
-      tma::bulk_store(smS + lo * N, buf, cnt * N * (unsigned)sizeof(double));
-      tma::bulk_store(sLS + lo * N * N, buf + S * N, cnt * N * N * (unsigned)sizeof(double));
-      tma::bulk_commit();
-      hi = lo;
-      ++t;
-    }
-    se = nxt;
-  }
-  tma::bulk_wait<0>();
-}
-
-template <int N, int NY, bool SMOOTH, class SRC>
-__global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
-k_filter_apply_tma(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
-                   const double* __restrict__ carry_m, const double* __restrict__ carry_L,
-                   const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
-                   const double* __restrict__ group_pref,
-                   double* __restrict__ fm, double* __restrict__ fL,
-                   double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
-                   unsigned int* __restrict__ counter, double* __restrict__ selems) {
-  using CF = tma::Cfg<N>;
-  constexpr int S = CF::SS, NBUF = CF::NB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* slice = reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * CF::LANE;
-
-  const long long seq = blockIdx.y;
-  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const long long Mw = Ppad / 32;
-  const long long k0 = c * K;
-  const long long k1 = (k0 + K < T) ? k0 + K : T;
-  if (SMOOTH && c == 0) counter[seq] = 0u;
-  Gauss<N> x;
-  load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
-  {
-    FElem<N> e;
-    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
-    filtering_apply<N>(x, e);
-    soa_load(warp_pref, seq, Mw, c / 32, e);
-    filtering_apply<N>(x, e);
-    soa_load(chunk_pref, seq, Ppad, c, e);
-    filtering_apply<N>(x, e);
-  }
-  double* fmS = fm + seq * (T + 1) * N;
-  double* fLS = fL + seq * (T + 1) * N * N;
-  if (c == 0) store_gauss_dense<N>(fmS, fLS, x);
-  double ell = 0.0;
-  SElem<N> sacc;
-  sacc.set_identity();
-  int t = 0;
-  long long lo = k0;  // first step of the current output tile
-#pragma unroll 1
-  for (long long k = k0; k < k1; ++k) {
-    const auto p = src.at(seq, k);
-    SElem<N> se;
-    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
-    const int slot = (int)(k - lo);
-    double* buf = slice + (t % NBUF) * CF::BUF_DOUBLES;
-    if (slot == 0) {  // first write into this buffer: the store issued NBUF tiles ago must have drained it
-      if (NBUF > 1) tma::bulk_wait_read<NBUF - 1>(); else tma::bulk_wait_read<0>();
-    }
-    store_gauss_smem<N>(buf + slot * N, buf + S * N + slot * N * N, x);
-    if (slot == S - 1 || k == k1 - 1) {
-      const unsigned cnt = (unsigned)(slot + 1);
-      tma::fence_proxy_async();
-      tma::bulk_store(fmS + (lo + 1) * N, buf, cnt * N * (unsigned)sizeof(double));
-      tma::bulk_store(fLS + (lo + 1) * N * N, buf + S * N, cnt * N * N * (unsigned)sizeof(double));
-      tma::bulk_commit();
-      lo = k + 1;
-      ++t;
-    }
-    if (SMOOTH) {
-      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
-      if (k == k0) sacc = se;
-      else sacc = smoothing_combine<N>(se, sacc);
-    }
-  }
-  if (ell_part) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
-    if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
-  }
-  if (SMOOTH) {
-    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
-    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
-    soa_store(chunk_suf, seq, Ppad, c, excl);
-    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
-  }
-  tma::bulk_wait<0>();
-}
-
-// ---- odd N: pair-staged factor stream (psqrt_tma.cuh, CfgOdd) --------------------------------
-template <int N>
-struct OddFactorStage {
-  double* slice;        // this lane's shared-memory slice: [NBUF][2][N*N]
-  double* gm;           // trajectory means   [*, N]
-  double* gL;           // trajectory factors [*, N, N]
-  long long first, last;  // inclusive index range this thread writes
-  int t;                // tiles handed to TMA so far
-
-  __device__ __forceinline__ void direct(long long idx, const Gauss<N>& x) const {
-    double* L = gL + idx * N * N;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) L[i * N + j] = (j <= i) ? x.Lc(i, j) : 0.0;
-  }
-  __device__ __forceinline__ void stage(int slot, const Gauss<N>& x) const {
-    double* b = slice + (t % tma::CfgOdd<N>::NBUF) * tma::CfgOdd<N>::PAIR + slot * N * N;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) b[i * N + j] = (j <= i) ? x.Lc(i, j) : 0.0;
-  }
-  __device__ __forceinline__ void flush(long long even_idx) {
-    tma::fence_proxy_async();
-    tma::bulk_store(gL + even_idx * N * N, slice + (t % tma::CfgOdd<N>::NBUF) * tma::CfgOdd<N>::PAIR,
-                    (unsigned)(tma::CfgOdd<N>::PAIR * sizeof(double)));
-    tma::bulk_commit();
-    ++t;
-  }
-  // ASC: indices arrive in increasing order; otherwise decreasing.
-  template <bool ASC>
-  __device__ __forceinline__ void put(long long idx, const Gauss<N>& x) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) gm[idx * N + i] = x.m[i];
-    const bool odd = idx & 1;
-    const bool paired = odd ? (idx - 1 >= first) : (idx + 1 <= last);
-    if (!paired) {
-      direct(idx, x);
-      return;
-    }
-    const bool opens = ASC ? !odd : odd;  // first record of its pair to arrive
-    if (opens) tma::bulk_wait_read<tma::CfgOdd<N>::NBUF - 1>();  // the buffer's previous tile has been drained
-    stage(odd ? 1 : 0, x);
-    if (!opens) flush(odd ? idx - 1 : idx);
-  }
-};
-
-template <int N>
-__global__ void __launch_bounds__(kBlock, PSQ_MINB_K5)
-k_smooth_apply_tma_odd(long long T, int K, long long Ppad,
-                       const double* __restrict__ carry_m, const double* __restrict__ carry_L,
-                       long long carry_mstride, long long carry_Lstride,
-                       const double* __restrict__ chunk_suf, const double* __restrict__ warp_suf,
-                       const double* __restrict__ group_suf, const double* __restrict__ selems,
-                       double* __restrict__ sm, double* __restrict__ sL, int write_terminal) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const long long seq = blockIdx.y;
-  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const long long Mw = Ppad / 32;
-  const long long k0 = c * K;
-  const long long k1 = (k0 + K < T) ? k0 + K : T;
-  if (k0 >= k1) return;
-  double* smS = sm + seq * (T + 1) * N;
-  double* sLS = sL + seq * (T + 1) * N * N;
-  OddFactorStage<N> st{reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * tma::CfgOdd<N>::LANE, smS, sLS, k0,
-                       k1 - 1, 0};
-  SElem<N> se;
-  selem_load<N>(selems, seq, K, Ppad, c, (int)(k1 - 1 - k0), se);
-  Gauss<N> xs;
-  load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
-  if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
-  {
-    SElem<N> e;
-    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);
-    smoothing_apply<N>(xs, e);
-    soa_load(warp_suf, seq, Mw, c / 32, e);
-    smoothing_apply<N>(xs, e);
-    soa_load(chunk_suf, seq, Ppad, c, e);
-    smoothing_apply<N>(xs, e);
-  }
-#pragma unroll 1
-  for (long long k = k1 - 1; k >= k0; --k) {
-    SElem<N> nxt;
-    if (k > k0) selem_load<N>(selems, seq, K, Ppad, c, (int)(k - 1 - k0), nxt);
-    smoothing_apply<N>(xs, se);
-    st.template put<false>(k, xs);
-    se = nxt;
-  }
-  tma::bulk_wait<0>();
-}
-
-template <int N, int NY, bool SMOOTH, class SRC>
-__global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
-k_filter_apply_tma_odd(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
-                       const double* __restrict__ carry_m, const double* __restrict__ carry_L,
-                       const double* __restrict__ chunk_pref, const double* __restrict__ warp_pref,
-                       const double* __restrict__ group_pref,
-                       double* __restrict__ fm, double* __restrict__ fL,
-                       double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
-                       unsigned int* __restrict__ counter, double* __restrict__ selems) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const long long seq = blockIdx.y;
-  const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  const long long Mw = Ppad / 32;
-  const long long k0 = c * K;
-  const long long k1 = (k0 + K < T) ? k0 + K : T;
-  if (SMOOTH && c == 0) counter[seq] = 0u;
-  Gauss<N> x;
-  load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
-  {
-    FElem<N> e;
-    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
-    filtering_apply<N>(x, e);
-    soa_load(warp_pref, seq, Mw, c / 32, e);
-    filtering_apply<N>(x, e);
-    soa_load(chunk_pref, seq, Ppad, c, e);
-    filtering_apply<N>(x, e);
-  }
-  double* fmS = fm + seq * (T + 1) * N;
-  double* fLS = fL + seq * (T + 1) * N * N;
-  if (c == 0) store_gauss_dense<N>(fmS, fLS, x);
-  OddFactorStage<N> st{reinterpret_cast<double*>(smem_raw) + (size_t)threadIdx.x * tma::CfgOdd<N>::LANE, fmS, fLS,
-                       k0 + 1, k1, 0};
-  double ell = 0.0;
-  SElem<N> sacc;
-  sacc.set_identity();
-#pragma unroll 1
-  for (long long k = k0; k < k1; ++k) {
-    const auto p = src.at(seq, k);
-    SElem<N> se;
-    ell += kalman_step<N, NY, SMOOTH>(x, p, &se);
-    st.template put<true>(k + 1, x);
-    if (SMOOTH) {
-      selem_store<N>(selems, seq, K, Ppad, c, (int)(k - k0), se);
-      if (k == k0) sacc = se;
-      else sacc = smoothing_combine<N>(se, sacc);
-    }
-  }
-  if (ell_part) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
-    if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
-  }
-  if (SMOOTH) {
-    SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
-    SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
-    soa_store(chunk_suf, seq, Ppad, c, excl);
-    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
-  }
-  tma::bulk_wait<0>();
 }
 
 // =========================================================================================

@@ -14,12 +14,13 @@ struct HostModel {
 };
 
 struct LaunchNY {
-  void (*filter_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, double* chunk_pref,
-                        double* warp_tot, unsigned int* counter, cudaStream_t);
+  void (*filter_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
+                        double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter, cudaStream_t);
   void (*filter_apply)(int smooth, const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
-                       const double* carry_m, const double* carry_L, const double* chunk_pref,
-                       const double* warp_pref, const double* group_pref, double* fm, double* fL, double* chunk_suf,
-                       double* warp_stot, double* ell_part, unsigned int* counter_s, double* selems, cudaStream_t);
+                       const double* carry_m, const double* carry_L, const double* chunk_own,
+                       const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
+                       double* fL, double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
+                       double* fpack, cudaStream_t);
   void (*filter_elements)(const SSMArgs&, long long T, long long B, const double* m0, const double* L0, double* A,
                           double* b, double* U, double* eta, double* Z, cudaStream_t);
   void (*loglik_terms)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* terms,
@@ -28,18 +29,18 @@ struct LaunchNY {
 
 struct LaunchN {
   int n;
-  int nf_filter, nf_smoother;
+  int nf_filter, nf_smoother, nf_state;
   const LaunchNY* (*for_ny)(int ny);
   void (*mid_filter)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                      cudaStream_t);
   void (*mid_smooth)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                      const double* ell_part, double* ell_out, cudaStream_t);
   void (*smooth_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, const double* fm,
-                        const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, double* selems,
+                        const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, double* fpack,
                         cudaStream_t);
-  void (*smooth_apply)(long long T, int K, long long Ppad, long long B, const double* carry_m,
-                       const double* carry_L, long long cms, long long cLs, const double* chunk_suf,
-                       const double* warp_suf, const double* group_suf, const double* selems,
+  void (*smooth_apply)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
+                       const double* carry_m, const double* carry_L, long long cms, long long cLs,
+                       const double* chunk_suf, const double* warp_suf, const double* group_suf, const double* fpack,
                        double* sm, double* sL, int write_terminal, cudaStream_t);
   void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                        double* cL, cudaStream_t);

@@ -37,10 +37,16 @@ PSQ_HD double rcp_nr(double d) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#if defined(PSQ_CUBIC_SEEDS)
+  // one cubic step: y (1 + e + e^2), e = 1 - d y  (seed error 2^-20 -> 2^-60; 3 dependent operations)
+  const double e = fma(-d, y, 1.0);
+  return fma(y, fma(e, e, e), y);
+#else
   double e = fma(-d, y, 1.0);
   y = fma(y, e, y);
   e = fma(-d, y, 1.0);
   return fma(y, e, y);
+#endif
 #else
   return 1.0 / d;
 #endif
@@ -49,11 +55,17 @@ PSQ_HD double rsqrt_nr(double d) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#if defined(PSQ_CUBIC_SEEDS)
+  // one Halley step: y (1 + r/2 + 3 r^2 / 8), r = 1 - d y^2  (seed error 2^-20 -> ~2^-58; 4 dependent operations)
+  const double r = fma(-(d * y), y, 1.0);
+  return fma(y * r, fma(0.375, r, 0.5), y);
+#else
   const double h = 0.5 * d;
   double r = fma(-(h * y), y, 0.5);
   y = fma(y, r, y);
   r = fma(-(h * y), y, 0.5);
   return fma(y, r, y);
+#endif
 #else
   return 1.0 / sqrt(d);
 #endif
@@ -247,6 +259,19 @@ struct StepVals {
   template <int NY_> PSQ_HD double fR(int a, int q) const { return m.R[a * NY + q]; }
   PSQ_HD double fc(int a) const { return m.c[a]; }
   PSQ_HD double fy(int a) const { return ldg(y + a); }
+};
+
+// Transition part only (backward sweep).
+template <int N>
+struct ModelValsT {
+  double F[N * N], Q[N * N], bq[N];
+};
+template <int N>
+struct StepValsT {
+  const ModelValsT<N>& m;
+  template <int N_> PSQ_HD double fF(int i, int j) const { return m.F[i * N + j]; }
+  template <int N_> PSQ_HD double fQ(int i, int j) const { return m.Q[i * N + j]; }
+  PSQ_HD double fb(int i) const { return m.bq[i]; }
 };
 
 // Shared by the Kalman update of both sweeps: given the predicted factor Np (lower, N x N,
@@ -479,6 +504,116 @@ PSQ_HD double kalman_step(Gauss<N>& x, const P& p, SElem<N>* se) {
   return -0.5 * quad - logdet - NY * kHalfLog2Pi;
 }
 
+// ---------------------------------------------------------------------------------------
+// The same Kalman step for the inside of a chunk, carrying ANY square root Y of the filtered
+// covariance (dense N x N) instead of the lower-triangular one.  Only NY reflectors of the update are
+// loop-carried: after them rows >= NY of tria's work array read [Psi21 | Y] with Y Y^T the posterior
+// covariance, which is all the next prediction tria([F Y | Q]) needs.  The remaining N - 1 reflectors
+// that make the OUTPUT factor lower triangular (_filtering.py:126-131 returns tria's triangle) are
+// software-pipelined: each call triangularises the state it was GIVEN (`in_tri`, the output of the
+// previous step) while it advances x by one step.  The two streams are independent, which is what lets
+// the in-order issue of a warp overlap the reflector of one with the rsqrt / rcp chain of the other.
+// LOGLIK = false skips the log-likelihood term (returns 0).
+// ---------------------------------------------------------------------------------------
+template <int N>
+struct GaussD {  // (mean, any dense square-root factor)
+  double m[N];
+  double Y[N][N];
+};
+
+template <int N>
+PSQ_HD void gaussd_tri(const GaussD<N>& x, Gauss<N>& out) {
+  double Yt[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    out.m[i] = x.m[i];
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) Yt[i][j] = x.Y[i][j];
+  }
+  house_rows<N, N, N - 1>(Yt);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) out.Lc(i, j) = Yt[i][j];
+}
+
+template <int N, int NY, bool LOGLIK, class P>
+PSQ_HD double kalman_step_dense(GaussD<N>& x, const P& p, Gauss<N>& in_tri) {
+  gaussd_tri<N>(x, in_tri);
+  double F[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
+  double mp[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = p.fb(i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], x.m[k], s);
+    mp[i] = s;
+  }
+  double M1[N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < N; ++k) u = fma(F[i][k], x.Y[k][j], u);
+      M1[i][j] = u;
+      M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
+    }
+  house_rows<N, 2 * N, N, N>(M1);
+  double M2[NY + N][N + NY];
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double h[N];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) h[k] = p.template fH<N>(a, k);
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double acc = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) acc = fma(h[k], M1[k][j], acc);
+      M2[a][j] = acc;
+    }
+    PSQ_UNROLL
+    for (int q = 0; q < NY; ++q) M2[a][N + q] = p.template fR<NY>(a, q);
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    PSQ_UNROLL
+    for (int j = 0; j < N + NY; ++j) M2[NY + i][j] = (j <= i) ? M1[i][j] : 0.0;
+  }
+  house_rows<NY + N, N + NY, NY>(M2);  // only Psi11 / Psi21; rows >= NY, columns >= NY: the factor Y
+  double inv2[NY], rr[NY];
+  psi11_inv_diag<N, NY>(M2, inv2);
+  double quad = 0.0, detS = 1.0;
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    double r = p.fy(a) - p.fc(a);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) r = fma(-p.template fH<N>(a, k), mp[k], r);
+    PSQ_UNROLL
+    for (int q = 0; q < a; ++q) r = fma(-M2[a][q], rr[q], r);
+    rr[a] = r * inv2[a];
+    quad = fma(rr[a], rr[a], quad);
+    detS *= M2[a][a];
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double mi = mp[i];
+    PSQ_UNROLL
+    for (int a = 0; a < NY; ++a) mi = fma(M2[NY + i][a], rr[a], mi);
+    x.m[i] = mi;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) x.Y[i][j] = M2[NY + i][NY + j];
+  }
+  if (!LOGLIK) return 0.0;
+  return -0.5 * quad - log(fabs(detS)) - NY * kHalfLog2Pi;
+}
+
 // Smoothing element of step k from the filtered state alone (used by sweep 3, which
 // recomputes instead of re-reading 8(2N^2+N) bytes per step).            _smoothing.py:72-85
 template <int N, class P>
@@ -624,7 +759,9 @@ PSQ_HD void filtering_combine_core(const FElem<N>* e1full, const double (&b1)[N]
       Xi[N + i][j] = (j <= i) ? e2.Z(i, j) : 0.0;
       Xi[N + i][N + j] = 0.0;
     }
-  house_rows<2 * N, 2 * N, N>(Xi);  // Xi11 = Xi[<N][<N] lower, Xi21 = Xi[N+.][<N], rest = pre-Xi22
+  // Xi11 = Xi[<N][<N] lower, Xi21 = Xi[N+.][<N], rest = pre-Xi22.  Row j of the top block [U1^T Z2 | I] has
+  // nothing right of column N + j (earlier reflectors only fill columns N .. N + j - 1): short reflectors.
+  house_rows<2 * N, 2 * N, N, N>(Xi);
   // T1 = Xi11^{-1} U1^T   (N x N; U1^T is upper triangular so T1[i][j] needs k <= ... dense in general)
   double inv[N];
   PSQ_UNROLL
@@ -976,6 +1113,177 @@ PSQ_HD double loglik_term(const StepPtrs& p, const double* m, const double* L) {
     logdet += log(fabs(S[a][a]));
   }
   return -0.5 * quad - logdet - NY * kHalfLog2Pi;
+}
+
+// ---------------------------------------------------------------------------------------
+// Chunk-level smoothing element.  For a run of steps k0 .. k1-1 whose filtering summary is
+// e = (A, b, U, eta, Z) (the ordered combine of its elements, _operators.py:58-77) and the filtered
+// state x = (m, L) at index k0, the ordered combine of the run's smoothing elements
+// (_operators.py:118-125) is the conditional  p(x_k0 | x_k1, y_{<k1}) = N(E x_k1 + g, D D^T).
+// It follows from the summary in two steps instead of k1 - k0 combines:
+//   (1) condition x_k0 on the run's observations, which enter through (eta, Z Z^T) exactly as in the
+//       filtering combine:  Xi = tria([[L^T Z, I], [Z, 0]]),  L' = L Xi11^{-T},
+//       m' = (I - L' Xi21^T)(m + L L^T eta);
+//   (2) one smoothing-element construction (_smoothing.py:72-85) for the "big step"
+//       x_k1 = A x_k0 + b + N(0, U U^T) from (m', L').
+// ---------------------------------------------------------------------------------------
+template <int N>
+struct ElemAsStep {  // presents a filtering summary as the linear model of one (big) step
+  const FElem<N>& e;
+  template <int N_> PSQ_HD double fF(int i, int j) const { return e.A(i, j); }
+  template <int N_> PSQ_HD double fQ(int i, int j) const { return e.U(i, j); }  // only j <= i is read
+  PSQ_HD double fb(int i) const { return e.b(i); }
+};
+
+template <int N>
+PSQ_HD void chunk_smoothing_total(const Gauss<N>& x, const FElem<N>& e, SElem<N>& out) {
+  double Xi[2 * N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = (i > j ? i : j); k < N; ++k) s = fma(x.Lc(k, i), e.Z(k, j), s);
+      Xi[i][j] = s;
+      Xi[i][N + j] = (i == j) ? 1.0 : 0.0;
+      Xi[N + i][j] = (j <= i) ? e.Z(i, j) : 0.0;
+      Xi[N + i][N + j] = 0.0;
+    }
+  house_rows<2 * N, 2 * N, N, N>(Xi);
+  double inv[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) inv[i] = rcp_nr(Xi[i][i]);
+  // T1 = Xi11^{-1} L^T, so that L' = T1^T
+  double T1[N][N];
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j)
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      double s = (j >= i) ? x.Lc(j, i) : 0.0;
+      PSQ_UNROLL
+      for (int k = 0; k < i; ++k) s = fma(-Xi[i][k], T1[k][j], s);
+      T1[i][j] = s * inv[i];
+    }
+  // m' = t - T1^T Xi21^T t,  t = m + L L^T eta
+  double t[N], u[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+    PSQ_UNROLL
+    for (int k = i; k < N; ++k) s = fma(x.Lc(k, i), e.eta(k), s);
+    u[i] = s;
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = x.m[i];
+    PSQ_UNROLL
+    for (int k = 0; k <= i; ++k) s = fma(x.Lc(i, k), u[k], s);
+    t[i] = s;
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(Xi[N + k][i], t[k], s);
+    u[i] = s;
+  }
+  Gauss<N> xp;
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = t[i];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(-T1[k][i], u[k], s);
+    xp.m[i] = s;
+  }
+  // lower-triangular factor of L' L'^T (the element construction reads a packed triangle)
+  double Lp[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) Lp[i][j] = T1[j][i];
+  house_rows<N, N, N - 1>(Lp);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) xp.Lc(i, j) = Lp[i][j];
+  smoothing_element<N>(xp, ElemAsStep<N>{e}, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// One RTS step of sweep 3: smoothed state at k from the smoothed state xs at k+1, the FILTERED
+// state xf at k and the model of step k.  Fuses the smoothing-element construction
+// (_smoothing.py:72-85) with the combine that applies it (_operators.py:118-125):
+//   tria([[F L, Q], [L, 0]]) = [[Phi11, 0], [Phi21, Phi22]],  E = Phi21 Phi11^{-1},
+//   m_s <- m + E (m_s - F m - b),   L_s <- tria([E L_s | Phi22]).
+// Phi22 enters the last triangularisation as left by the first one (dense N x N): triangularising
+// it on its own first, as the element-level seam does, would not change L_s L_s^T.
+// ---------------------------------------------------------------------------------------
+template <int N, class P>
+PSQ_HD void rts_step(Gauss<N>& xs, const Gauss<N>& xf, const P& p) {
+  double F[N][N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) F[i][j] = p.template fF<N>(i, j);
+  double dm[N];  // m_s(k+1) - (F m + b)
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double s = xs.m[i] - p.fb(i);
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) s = fma(-F[i][k], xf.m[k], s);
+    dm[i] = s;
+  }
+  double M1[2 * N][2 * N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double u = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) u = fma(F[i][k], xf.Lc(k, j), u);
+      M1[i][j] = u;
+      M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
+    }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i)
+    PSQ_UNROLL
+    for (int j = 0; j < 2 * N; ++j) M1[N + i][j] = (j <= i) ? xf.Lc(i, j) : 0.0;
+  house_rows<2 * N, 2 * N, N, N>(M1);
+  double inv[N];
+  PSQ_UNROLL
+  for (int j = 0; j < N; ++j) inv[j] = rcp_nr(M1[j][j]);
+  double W[N][2 * N], mn[N];
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    double E[N];
+    PSQ_UNROLL
+    for (int j = N - 1; j >= 0; --j) {
+      double s = M1[N + i][j];
+      PSQ_UNROLL
+      for (int k = j + 1; k < N; ++k) s = fma(-E[k], M1[k][j], s);
+      E[j] = s * inv[j];
+    }
+    double mi = xf.m[i];
+    PSQ_UNROLL
+    for (int k = 0; k < N; ++k) mi = fma(E[k], dm[k], mi);
+    mn[i] = mi;
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double d = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) d = fma(E[k], xs.Lc(k, j), d);
+      W[i][j] = d;
+      W[i][N + j] = M1[N + i][N + j];
+    }
+  }
+  house_rows<N, 2 * N, N>(W);
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    xs.m[i] = mn[i];
+    PSQ_UNROLL
+    for (int j = 0; j <= i; ++j) xs.Lc(i, j) = W[i][j];
+  }
 }
 
 // Rank-one Cholesky update, literal column sweep of _utils.py:39-81 (incl. the

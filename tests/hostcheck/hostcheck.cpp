@@ -55,13 +55,14 @@ template <int N, int NY>
 int pass(const HSsm& a, long long T, int K, const double* m0, const double* L0, double* fm, double* fL, double* sm,
          double* sL, double* ell_out) {
   const long long P = (T + K - 1) / K, Ppad = (P + 127) / 128 * 128, M = Ppad / 32;
-  std::vector<FElem<N>> chunk_pref(Ppad), warp_tot(M);
+  std::vector<FElem<N>> chunk_pref(Ppad), chunk_own(Ppad), warp_tot(M);
   for (long long w = 0; w < M; ++w) {
     FElem<N> lanes[32];
     for (int l = 0; l < 32; ++l) {
       long long c = w * 32 + l, k0 = c * K, k1 = std::min<long long>(T, k0 + K);
       lanes[l].set_identity();
       for (long long k = k0; k < k1; ++k) filter_reduce_step<N, NY>(lanes[l], sp(a, k));
+      chunk_own[c] = lanes[l];
     }
     ks_scan(lanes, false);
     for (int l = 0; l < 32; ++l) {
@@ -83,12 +84,14 @@ int pass(const HSsm& a, long long T, int K, const double* m0, const double* L0, 
       filtering_apply<N>(x, warp_tot[w]);
       filtering_apply<N>(x, chunk_pref[c]);
       if (c == 0) store_dense<N>(fm, fL, x);
-      lanes[l].set_identity();
-      for (long long k = k0; k < k1; ++k) {
-        SElem<N> se;
-        ell += kalman_step<N, NY, true>(x, sp(a, k), &se);
-        store_dense<N>(fm + (k + 1) * N, fL + (k + 1) * N * N, x);
-        lanes[l] = (k == k0) ? se : smoothing_combine<N>(se, lanes[l]);
+      // the chunk's smoothing total straight from its filtering summary (no per-step combines)
+      if (k0 < k1) chunk_smoothing_total<N>(x, chunk_own[c], lanes[l]); else lanes[l].set_identity();
+      // inside the chunk the recursion carries a dense factor; x receives the triangular outputs
+      GaussD<N> xd;
+      for (int i = 0; i < N; ++i) { xd.m[i] = x.m[i]; for (int j = 0; j < N; ++j) xd.Y[i][j] = j <= i ? x.Lc(i, j) : 0.0; }
+      for (long long k = k0; k <= k1 && k0 < k1; ++k) {   // step k also triangularises the state at index k
+        if (k < k1) ell += kalman_step_dense<N, NY, true>(xd, sp(a, k), x); else gaussd_tri<N>(xd, x);
+        if (k > k0) store_dense<N>(fm + k * N, fL + k * N * N, x);
       }
     }
     ks_scan(lanes, true);
@@ -112,10 +115,7 @@ int pass(const HSsm& a, long long T, int K, const double* m0, const double* L0, 
     smoothing_apply<N>(xs, chunk_suf[c]);
     for (long long k = k1 - 1; k >= k0; --k) {
       Gauss<N> xf; load_dense<N>(fm + k * N, fL + k * N * N, xf);
-      SElem<N> se;
-      StepPtrs p = sp(a, k);
-      smoothing_element<N>(xf, p, se);
-      smoothing_apply<N>(xs, se);
+      rts_step<N>(xs, xf, sp(a, k));
       store_dense<N>(sm + k * N, sL + k * N * N, xs);
     }
   }
