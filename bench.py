@@ -43,6 +43,37 @@ def algorithmic_bytes_per_step(n):
     return 8 * (7 * n * n + 5 * n)
 
 
+def algorithmic_flops_per_step(n):
+    """one filtering combine (28.33 n^3 + 22 n^2) + one smoothing combine (7.33 n^3 + 2 n^2)."""
+    return 35.67 * n ** 3 + 24 * n ** 2
+
+
+def measure_fp64_peak(dev):
+    """FP64 FMA throughput of this GPU measured live with the library's probe kernel (independent DFMA
+    chains, 16 warps per SM): TFLOP/s.  SURVEY.md 8(d): the FP64 peak is not in MEASURED_PEAKS.json."""
+    import ctypes
+    import torch
+    from psqrt import _lib
+    lib = _lib.load()
+    if not hasattr(lib, "psqrt_fp64_probe"):
+        return None
+    out = torch.empty(148 * 512, dtype=torch.float64, device=dev)
+    iters = 20000
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.psqrt_fp64_probe(ctypes.c_void_p(out.data_ptr()), ctypes.c_int(iters), ctypes.byref(flops), st)
+        e1.record()
+        torch.cuda.synchronize()
+        if rc != 0:
+            return None
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 def make_lgssm(n, ny, seed=0):
     rng = np.random.RandomState(seed)
     Qr, _ = np.linalg.qr(rng.randn(n, n))
@@ -346,12 +377,28 @@ def run_psqrt(args):
         tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # from the committed ncu --set full capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)
+        fp64_peak = measure_fp64_peak(dev)
+        fp64_src = "measured live (psqrt_fp64_probe: independent DFMA chains, 16 warps/SM)"
+        if fp64_peak is None:
+            fp64_peak, fp64_src = 37.2, "nominal (148 SMs x 64 FMA/clk x 2 x 1.965 GHz)"
+        steps_per_s = T / (ms_per_step * 1e-3)
+        fp64_achieved = algorithmic_flops_per_step(NX) * steps_per_s / 1e12
+        hbm_bound = peak * 1e9 / algorithmic_bytes_per_step(NX)
+        fp64_bound = fp64_peak * 1e12 / algorithmic_flops_per_step(NX)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_step": share[dom], "stage_ms": stages,
                     "whole_pass": {"algorithmic_bytes_per_step": algorithmic_bytes_per_step(NX),
                                    "achieved": pass_achieved, "frac": pass_achieved / peak,
-                                   "note": "per GPU; B(n) = 8(7n^2+5n) canonical bytes per step / time of the whole pass"}}
+                                   "note": "per GPU; B(n) = 8(7n^2+5n) canonical bytes per step / time of the whole pass"},
+                    "fp64": {"algorithmic_flops_per_step": algorithmic_flops_per_step(NX), "achieved": fp64_achieved,
+                             "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+                             "peak_source": fp64_src},
+                    "north_star": {"steps_per_s": steps_per_s, "hbm_bound_steps_per_s": hbm_bound,
+                                   "fp64_bound_steps_per_s": fp64_bound,
+                                   "frac_of_slower_bound": steps_per_s / min(hbm_bound, fp64_bound),
+                                   "note": "BASELINE.json: fraction of min(HBM bound on canonical element bytes, FP64 "
+                                           "bound on canonical combine flops)"}}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) -----------------------------
     cpu_baseline = None

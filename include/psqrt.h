@@ -181,6 +181,13 @@ int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id
                             const double* nom_L, int64_t count, const double* m_q, const double* chol_q,
                             double* F, double* chol, double* b, void* stream);
 
+/* ---- measurement aid (bench.py): FP64 FMA throughput probe ------------------------------------
+ * Launches 148 x 4 CTAs of 128 threads, each thread running 8 independent chains of `iters` x 16 dependent
+ * DFMAs, and writes the flop count of the launch to *flops_out (host).  The caller times the launch with
+ * CUDA events: flops / seconds is the FP64 roofline denominator SURVEY.md 8(d) asks to be measured.
+ * out: device scratch of at least 148 * 512 doubles. */
+int psqrt_fp64_probe(double* out, int iters, double* flops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,24 @@
 #include "psqrt_launch.h"
 
 namespace psq {
+// FP64 FMA throughput probe (psqrt_fp64_probe): 8 independent dependent-DFMA chains per thread
+__global__ void __launch_bounds__(128) k_fp64_probe(double* out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
   k_ell_sum<0><<<(unsigned)B, 256, 0, st>>>(ell_part, M, ell_out);
 }
@@ -400,6 +418,14 @@ int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t b
   if (!ln) return PSQRT_EUNSUPPORTED;
   if (!A || !L || cols <= 0 || batch <= 0) return PSQRT_EINVAL;
   ln->tria(A, L, cols, batch, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_fp64_probe(double* out, int iters, double* flops_out, void* stream) {
+  if (!out || iters <= 0) return PSQRT_EINVAL;
+  const int ctas = 148 * 4, threads = 128;
+  psq::k_fp64_probe<<<ctas, threads, 0, (cudaStream_t)stream>>>(out, iters, 0.999, 1e-3);
+  if (flops_out) *flops_out = 2.0 * 8.0 * 16.0 * (double)iters * (double)ctas * (double)threads;
   return check_launch();
 }
 

@@ -84,14 +84,14 @@ struct NYImpl {
     launch_sweep(k_filter_reduce<N, NY, SrcPtr>, ysmem, Ppad, B, st, SrcPtr{a}, T, K, Ppad, chunk_own, chunk_pref,
                  warp_tot, counter);
   }
-  template <bool SMOOTH, class SRC>
+  template <bool SMOOTH, bool LOGLIK, class SRC>
   static void filter_apply_t(const SRC& src, long long T, int K, long long Ppad, long long B, const double* cm,
                              const double* cL, const double* chunk_own, const double* chunk_pref,
                              const double* warp_pref, const double* group_pref, double* fm, double* fL,
                              double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
                              double* fpack, cudaStream_t st) {
 #define PSQ_K3(OUT)                                                                                                  \
-  launch_sweep(k_filter_apply<N, NY, SMOOTH, SRC, OUT>, OUT::smem_bytes(kBlock) + LaneRing<NY, kYDepth>::smem_bytes(kBlock), Ppad, B, st, src, T, K, Ppad, cm, \
+  launch_sweep(k_filter_apply<N, NY, SMOOTH, LOGLIK, SRC, OUT>, OUT::smem_bytes(kBlock) + LaneRing<NY, kYDepth>::smem_bytes(kBlock), Ppad, B, st, src, T, K, Ppad, cm, \
                cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s, \
                fpack)
     if constexpr (N % 2 == 0) {
@@ -106,8 +106,14 @@ struct NYImpl {
                            double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
                            unsigned int* counter_s, double* fpack, cudaStream_t st) {
 #define PSQ_FA(SM, SRCV)                                                                                             \
-  filter_apply_t<SM>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, \
-                     warp_stot, ell_part, counter_s, fpack, st)
+  do {                                                                                                               \
+    if (ell_part)                                                                                                    \
+      filter_apply_t<SM, true>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL,   \
+                               chunk_suf, warp_stot, ell_part, counter_s, fpack, st);                                \
+    else                                                                                                             \
+      filter_apply_t<SM, false>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL,  \
+                                chunk_suf, warp_stot, ell_part, counter_s, fpack, st);                               \
+  } while (0)
     if constexpr (kByValue) {
       if (hm) {
         const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
@@ -153,12 +159,12 @@ inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31)
 
 void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 cudaStream_t st) {
-  k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, nullptr,
+  k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32 * Split<FElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, nullptr,
                                                            nullptr);
 }
 void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 const double* ell_part, double* ell_out, cudaStream_t st) {
-  k_mid_scan<SElem<N>, true><<<mid_grid(M, B), 32, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, ell_part,
+  k_mid_scan<SElem<N>, true><<<mid_grid(M, B), 32 * Split<SElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, ell_part,
                                                           ell_out);
 }
 void smooth_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,

@@ -328,69 +328,150 @@ __device__ __forceinline__ void soa_load_cg(const double* buf, long long seq, lo
   for (int f = 0; f < Elem::NF; ++f) e.v[f] = __ldcg(p + f * n_items);
 }
 
+// The mid-level scans are pure latency: a dozen dependent combines by a handful of warps while the rest
+// of the GPU idles.  Each combine is therefore split over the R warps of the CTA by OUTPUT field: every
+// warp holds the same 32 elements, runs its own inlined copy of the combine from which the compiler
+// removes everything its fields do not need (the three triangularisations of the filtering combine end up
+// in three different warps), and the pieces are exchanged through shared memory.
+template <class Elem>
+struct Split;
+template <int N>
+struct Split<FElem<N>> {  // 0: (b, U)   1: Z   2: (A, eta)
+  static constexpr int R = 3;
+  static __host__ __device__ constexpr int owner(int f) {
+    constexpr int TRI = N * (N + 1) / 2;
+    return f < N * N ? 2 : (f < N * N + N + TRI ? 0 : (f < N * N + 2 * N + TRI ? 2 : 1));
+  }
+};
+template <int N>
+struct Split<SElem<N>> {  // the smoothing combine is small: one warp, inlined (measured: splitting it loses)
+  static constexpr int R = 1;
+  static __host__ __device__ constexpr int owner(int) { return 0; }
+};
+
+// out = combine(a, b) computed by the R warps together; every warp gets the full result.  Must be called
+// by the whole CTA.  sm: [NF][32] doubles.  Deliberately not inlined (see k_mid_scan).
+template <class Elem>
+__device__ __noinline__ void combine_split_impl(const Elem& a, const Elem& b, Elem& out, double* sm, int role, int lane) {
+#pragma unroll
+  for (int r = 0; r < Split<Elem>::R; ++r) {
+    if (role == r) {
+      const Elem t = ScanOp<Elem>::combine(a, b);
+#pragma unroll
+      for (int f = 0; f < Elem::NF; ++f)
+        if (Split<Elem>::owner(f) == r) sm[f * 32 + lane] = t.v[f];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int f = 0; f < Elem::NF; ++f) out.v[f] = sm[f * 32 + lane];
+  __syncthreads();
+}
+template <class Elem>
+__device__ __forceinline__ void combine_split(const Elem& a, const Elem& b, Elem& out, double* sm, int role, int lane) {
+  if constexpr (Split<Elem>::R == 1) out = ScanOp<Elem>::combine(a, b);
+  else combine_split_impl<Elem>(a, b, out, sm, role, lane);
+}
+
+// Straight-line code that runs once is expensive here: a cold instruction fetch costs ~0.2 us per KB
+// (ncu: the last CTA's extra inlined copies of the combine took longer than the five warm Kogge-Stone
+// steps before them).  combine_split is therefore NOT inlined: level B and the three phases of level C
+// all run the same (per-role) copy of the combine, which is warm in the instruction cache after the first
+// Kogge-Stone step.
+template <class Elem>
+__device__ __forceinline__ Elem scan_inclusive_split(Elem e, double* sm, int role, int lane) {
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    const Elem o = shfl_elem<Elem, false>(e, d);
+    Elem c;
+    combine_split<Elem>(o, e, c, sm, role, lane);
+    if (lane >= d) e = c;
+  }
+  return e;
+}
+
 template <class Elem, bool REV>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * Split<Elem>::R, 1)
 k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ groups, long long G,
            unsigned int* __restrict__ counter, double* __restrict__ total_out,
            const double* __restrict__ ell_part, double* __restrict__ ell_out) {
+  __shared__ double sm[Split<Elem>::R > 1 ? Elem::NF * 32 : 1];
+  __shared__ unsigned int s_ticket;
   const long long seq = blockIdx.y;
   const long long g = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;
   {
     const long long sidx = g * 32 + lane;
     const long long i = REV ? (M - 1 - sidx) : sidx;
     Elem e;
     e.set_identity();
     if (sidx < M) soa_load(items, seq, M, i, e);
-    Elem incl = warp_scan_inclusive<Elem, false>(e, lane);
+    Elem incl = scan_inclusive_split<Elem>(e, sm, role, lane);
     Elem excl = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
-    if (sidx < M) soa_store(items, seq, M, i, excl);
-    if (lane == 31) soa_store(groups, seq, G, g, incl);
+    if (role == 0) {
+      if (sidx < M) soa_store(items, seq, M, i, excl);
+      if (lane == 31) soa_store(groups, seq, G, g, incl);
+    }
   }
+  if (role == 0) {
+    __threadfence();
+    if (lane == 0) s_ticket = atomicAdd(counter + seq, 1u);
+  }
+  __syncthreads();
+  if (s_ticket != (unsigned int)(G - 1)) return;
   __threadfence();
-  unsigned int ticket = 0;
-  if (lane == 0) ticket = atomicAdd(counter + seq, 1u);
-  ticket = __shfl_sync(kFull, ticket, 0);
-  if (ticket != (unsigned int)(G - 1)) return;
-  __threadfence();
-  const long long q = (G + 31) / 32;
+  // level C: this CTA finished last; lane l owns the q consecutive group totals [l q, l q + q)
+  const int q = (int)((G + 31) / 32);
   const long long s0 = (long long)lane * q;
-  const long long s1 = (s0 + q < G) ? s0 + q : G;
   Elem acc;
   acc.set_identity();
 #pragma unroll 1
-  for (long long sidx = s0; sidx < s1; ++sidx) {
+  for (int i = 0; i < q; ++i) {
     Elem x;
-    soa_load_cg(groups, seq, G, sidx, x);
-    acc = (sidx == s0) ? x : ScanOp<Elem>::combine(acc, x);
+    x.set_identity();
+    if (s0 + i < G) soa_load_cg(groups, seq, G, s0 + i, x);
+    if (i == 0) {
+      acc = x;
+    } else {
+      Elem c;
+      combine_split<Elem>(acc, x, c, sm, role, lane);
+      if (s0 + i < G) acc = c;
+    }
   }
-  Elem incl = warp_scan_inclusive<Elem, false>(acc, lane);
+  Elem incl = scan_inclusive_split<Elem>(acc, sm, role, lane);
   Elem run = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
-  if (lane == 31 && total_out) {
+  if (role == 0 && lane == 31 && total_out) {
 #pragma unroll
     for (int f = 0; f < Elem::NF; ++f) total_out[seq * Elem::NF + f] = incl.v[f];
   }
 #pragma unroll 1
-  for (long long sidx = s0; sidx < s1; ++sidx) {
+  for (int i = 0; i < q; ++i) {
     Elem x;
-    soa_load_cg(groups, seq, G, sidx, x);
-    soa_store(groups, seq, G, sidx, run);
-    if (sidx + 1 < s1) run = ScanOp<Elem>::combine(run, x);
+    x.set_identity();
+    if (s0 + i < G) soa_load_cg(groups, seq, G, s0 + i, x);
+    __syncthreads();   // every warp has read the total before warp 0 overwrites it with the prefix
+    if (role == 0 && s0 + i < G) soa_store(groups, seq, G, s0 + i, run);
+    if (i + 1 < q) {
+      Elem c;
+      combine_split<Elem>(run, x, c, sm, role, lane);
+      run = c;
+    }
   }
-  if (ell_part) {
+  if (ell_part && role == 0) {
     double sum = 0.0;
     for (long long i = lane; i < M; i += 32) sum += ell_part[seq * M + i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(kFull, sum, d);
     if (lane == 0) ell_out[seq] = sum;
   }
-  if (lane == 0) counter[seq] = 0u;
+  if (threadIdx.x == 0) counter[seq] = 0u;
 }
 
 // =========================================================================================
 // K3
 // =========================================================================================
-template <int N, int NY, bool SMOOTH, class SRC, class OUT>
+template <int N, int NY, bool SMOOTH, bool LOGLIK, class SRC, class OUT>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K3)
 k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Ppad,
                const double* __restrict__ carry_m, const double* __restrict__ carry_L,  // [B][N], [B][N][N] lower
@@ -413,13 +494,15 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   for (int d = 0; d < kYDepth; ++d) yring.issue(d, k0 + d < k1, src.yp(seq, k0 + d), 1);
   Gauss<N> x;
   load_gauss_dense<N>(carry_m + seq * N, carry_L + seq * N * N, x);
-  {
+  // carry pushed through the three exclusive prefixes (group, warp, chunk).  A loop, not three inlined
+  // copies: code that runs once per kernel is paid for in cold instruction fetches (see k_mid_scan).
+#pragma unroll 1
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    const double* buf = (lvl == 0) ? group_pref : (lvl == 1) ? warp_pref : chunk_pref;
+    const long long n_items = (lvl == 0) ? (Mw + 31) / 32 : (lvl == 1) ? Mw : Ppad;
+    const long long idx = (lvl == 0) ? c / 1024 : (lvl == 1) ? c / 32 : c;
     FElem<N> e;
-    soa_load(group_pref, seq, (Mw + 31) / 32, c / 1024, e);
-    filtering_apply<N>(x, e);
-    soa_load(warp_pref, seq, Mw, c / 32, e);
-    filtering_apply<N>(x, e);
-    soa_load(chunk_pref, seq, Ppad, c, e);
+    soa_load(buf, seq, n_items, idx, e);
     filtering_apply<N>(x, e);
   }
   double* fmS = fm + seq * (T + 1) * N;
@@ -467,8 +550,7 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
         yring.issue(slot, j + kYDepth < len, src.yp(seq, k + kYDepth), 1);
         slot = (slot + 1 == kYDepth) ? 0 : slot + 1;
         const auto p = src.at(seq, k);
-        if (ell_part) ell += kalman_step_dense<N, NY, true>(xd, WithY<decltype(p), NY>{p, ycur}, x);
-        else kalman_step_dense<N, NY, false>(xd, WithY<decltype(p), NY>{p, ycur}, x);
+        ell += kalman_step_dense<N, NY, LOGLIK>(xd, WithY<decltype(p), NY>{p, ycur}, x);
         if (SMOOTH) fpack_store<N>(fpack, seq, K, Ppad, c, j, x);  // filtered state at index k
       } else if (j == len) {
         gaussd_tri<N>(xd, x);
@@ -476,7 +558,7 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
       if (j > 0) out.put(j, j <= len, x);  // trajectory index k0 + j
     }
   }
-  if (ell_part) {
+  if (LOGLIK) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) ell += __shfl_down_sync(kFull, ell, d);
     if (lane == 0) ell_part[seq * Mw + c / 32] = ell;
@@ -548,13 +630,15 @@ k_smooth_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   if (len > 0) {
     load_gauss_dense<N>(carry_m + seq * carry_mstride, carry_L + seq * carry_Lstride, xs);
     if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
-    SElem<N> e;
-    soa_load(group_suf, seq, (Mw + 31) / 32, (Mw - 1 - c / 32) / 32, e);  // groups are in scan (reverse) order
-    smoothing_apply<N>(xs, e);
-    soa_load(warp_suf, seq, Mw, c / 32, e);
-    smoothing_apply<N>(xs, e);
-    soa_load(chunk_suf, seq, Ppad, c, e);
-    smoothing_apply<N>(xs, e);
+#pragma unroll 1
+    for (int lvl = 0; lvl < 3; ++lvl) {   // terminal state pushed through the three exclusive suffixes
+      const double* buf = (lvl == 0) ? group_suf : (lvl == 1) ? warp_suf : chunk_suf;
+      const long long n_items = (lvl == 0) ? (Mw + 31) / 32 : (lvl == 1) ? Mw : Ppad;
+      const long long idx = (lvl == 0) ? (Mw - 1 - c / 32) / 32 : (lvl == 1) ? c / 32 : c;  // groups: scan (reverse) order
+      SElem<N> e;
+      soa_load(buf, seq, n_items, idx, e);
+      smoothing_apply<N>(xs, e);
+    }
   }
   OUT out(smem_raw, smS, sLS, c, K, T, 0);
   int slot = 0;

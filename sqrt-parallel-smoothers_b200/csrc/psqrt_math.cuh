@@ -30,14 +30,16 @@ namespace psq {
 
 constexpr double kHalfLog2Pi = 0.91893853320467274178;  // log(2*pi)/2
 
-// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, >= 20
-// good bits) + two Newton steps -> ~1 ulp, no slow-path call.  Inputs here are norms and diagonal
-// entries of factors; 0 gives NaN/inf exactly where the reference's division does.
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20
+// relative error) + ONE cubically convergent step -> below 2^-57, no slow-path call.  The cubic step is
+// one or two dependent operations shorter than two Newton steps, and these chains sit on the critical
+// path of every reflector (-DPSQ_NEWTON_SEEDS restores the two Newton steps).  Inputs here are norms and
+// diagonal entries of factors; 0 gives NaN/inf exactly where the reference's division does.
 PSQ_HD double rcp_nr(double d) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-#if defined(PSQ_CUBIC_SEEDS)
+#if !defined(PSQ_NEWTON_SEEDS)
   // one cubic step: y (1 + e + e^2), e = 1 - d y  (seed error 2^-20 -> 2^-60; 3 dependent operations)
   const double e = fma(-d, y, 1.0);
   return fma(y, fma(e, e, e), y);
@@ -55,7 +57,7 @@ PSQ_HD double rsqrt_nr(double d) {
 #if defined(__CUDA_ARCH__)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-#if defined(PSQ_CUBIC_SEEDS)
+#if !defined(PSQ_NEWTON_SEEDS)
   // one Halley step: y (1 + r/2 + 3 r^2 / 8), r = 1 - d y^2  (seed error 2^-20 -> ~2^-58; 4 dependent operations)
   const double r = fma(-(d * y), y, 1.0);
   return fma(y * r, fma(0.375, r, 0.5), y);

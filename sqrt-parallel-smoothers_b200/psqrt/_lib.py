@@ -42,6 +42,7 @@ EXPORTS = (
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
+    "psqrt_fp64_probe",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
