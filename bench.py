@@ -262,10 +262,38 @@ def run_psqrt(args):
 
     if world > 1:
         from psqrt import dist as pdist
-        sharded = pdist.TimeShardedSmoother(NX, NY, T, device=dev)
+        sharded = pdist.TimeShardedSmoother(NX, NY, T, device=dev, exchange=os.environ.get("PSQRT_EXCHANGE", "peer"))
 
-        def one_pass():
-            return sharded.filter_smoother(ssm, ys[None], m0[None], L0[None])
+        yb_, m0b_, L0b_ = ys[None].contiguous(), m0[None].contiguous(), L0[None].contiguous()
+
+        def eager_pass():
+            return sharded.filter_smoother(ssm, yb_, m0b_, L0b_)
+
+        one_pass = eager_pass
+        graph_note = "eager launches"
+        if os.environ.get("PSQRT_GRAPH", "1") != "0":
+            # the host side of a sharded pass (11 launches + tensor bookkeeping through ctypes) costs more than the
+            # GPU work it feeds: capture the pass once, replay it per step.  Exchanges are kernels (peer mode) or
+            # NCCL collectives (capturable), epochs live on the device.
+            try:
+                for _ in range(3):
+                    eager_pass()
+                torch.cuda.synchronize()
+                dist.barrier()
+                if sharded.exchange != "peer":     # NCCL collectives inside a capture hung on this pool: stay eager
+                    raise RuntimeError("exchange is NCCL")
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    graph_out = eager_pass()
+                torch.cuda.synchronize()
+
+                def one_pass():
+                    graph.replay()
+                    return graph_out
+                graph_note = "one CUDA graph per pass"
+            except Exception as e:       # capture not possible on this system: eager launches
+                graph_note = f"eager launches ({e})"
+                one_pass = eager_pass
     else:
         def one_pass():
             return _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=False, chunk_len=args.chunk)
@@ -416,14 +444,20 @@ def run_psqrt(args):
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C1 random stable LGSSM nx=4 ny=2, T=1e6 steps per GPU, one sqrt parallel "
+            "config": {"workload": f"C1 random stable LGSSM nx={NX} ny={NY}, T={T:.0e} steps per GPU, one sqrt parallel "
                                    "filter_smoother pass per step" + (", time-sharded over the GPUs with 2 NCCL "
                                                                       "all-gathers of shard totals" if world > 1 else ""),
                        "nx": NX, "ny": NY, "T_per_gpu": T, "T_total": T * world, "chunk_len": plan.chunk_len,
                        "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
+                       "launch": (graph_note if world > 1 else "eager launches"),
+                       "exchange": (None if world == 1 else
+                                    ("P2P stores into peer-mapped buffers + flags (psqrt_peer_push / psqrt_peer_wait)"
+                                     if sharded.exchange == "peer" else
+                                     "NCCL all-gather x2" + (f" (peer exchange unavailable: {sharded.exchange_error})"
+                                                             if sharded.exchange_error else ""))),
                        "l2": "working set per pass (y 16 MB + filtered 160 MB + smoothed 160 MB) exceeds the 126 MB L2; "
                              "no explicit flush"},
-            "e2e": e2e, "gpu_launches": (5 if world == 1 else 7) * args.steps,
+            "e2e": e2e, "gpu_launches": (5 if world == 1 else (11 if sharded.exchange == "peer" else 7)) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
@@ -488,7 +522,14 @@ def main():
     ap.add_argument("--workload", default="lgssm", choices=["lgssm", "bearings"],
                     help="lgssm = the driver's metric; bearings = informational configs[1] line")
     ap.add_argument("--lin", default="extended", choices=["extended", "cubature", "gauss_hermite"])
+    ap.add_argument("--nx", type=int, default=4, help="state dimension of the LGSSM workload (informational runs; "
+                                                      "the driver's metric is the default nx=4, ny=2)")
+    ap.add_argument("--ny", type=int, default=2)
     args = ap.parse_args()
+    global NX, NY, METRIC
+    if (args.nx, args.ny) != (NX, NY):
+        NX, NY = args.nx, args.ny
+        METRIC = METRIC.replace("nx=4", f"nx={NX}")
     if args.workload == "bearings":
         return run_bearings(args)
     if args.impl == "reference":

@@ -181,6 +181,27 @@ int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id
                             const double* nom_L, int64_t count, const double* m_q, const double* chol_q,
                             double* F, double* chol, double* b, void* stream);
 
+/* ---- time-shard exchange over peer-mapped memory (NVLink / NVSwitch P2P) --------------------------------
+ * The shard totals a time-sharded pass exchanges are a few hundred bytes: an NCCL all-gather
+ * costs its launch + protocol latency (~20 us) twice per pass.  With every rank's exchange buffer mapped into
+ * every peer (CUDA IPC / symmetric memory), psqrt_peer_push stores this rank's contribution straight into slot
+ * `rank` of EVERY peer's buffer and then raises that peer's flag word; psqrt_peer_wait spins (on the GPU, in
+ * stream order) until the flags of ranks [first, last] have reached `epoch`.  The carry kernels
+ * (psqrt_carry_filter / psqrt_carry_smoother) then read the totals from the local buffer.
+ *   peer_bufs  DEVICE array of n_ranks pointers: base of each peer's exchange buffer (doubles)
+ *   peer_flags DEVICE array of n_ranks pointers: base of each peer's flag array (n_ranks 64-bit words, zeroed once)
+ *   up to three segments (src[i], count[i] doubles) go to peer offsets dst_off[i] (doubles; slot of THIS rank)
+ * Flags are monotonic epochs, so nothing is ever reset.  The epoch lives on the device (`epoch_ctr`, one 64-bit
+ * word per exchange, zeroed once): a push publishes *epoch_ctr + 1, the wait that follows it in stream order
+ * waits for that value and then stores it back -- no per-pass host argument, so a whole time-sharded pass
+ * can be captured in a CUDA graph and replayed. */
+int psqrt_peer_push(const double* src0, int64_t count0, int64_t dst_off0, const double* src1, int64_t count1,
+                    int64_t dst_off1, const double* src2, int64_t count2, int64_t dst_off2,
+                    double* const* peer_bufs, unsigned long long* const* peer_flags, int rank, int n_ranks,
+                    const unsigned long long* epoch_ctr, void* stream);
+int psqrt_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr,
+                    void* stream);
+
 /* ---- measurement aid (bench.py): FP64 FMA throughput probe ------------------------------------
  * Launches 148 x 4 CTAs of 128 threads, each thread running 8 independent chains of `iters` x 16 dependent
  * DFMAs, and writes the flop count of the launch to *flops_out (host).  The caller times the launch with

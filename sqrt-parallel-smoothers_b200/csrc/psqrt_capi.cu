@@ -27,6 +27,39 @@ __global__ void __launch_bounds__(128) k_fp64_probe(double* out, int iters, doub
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Time-shard exchange over peer-mapped memory (psqrt_peer_push / psqrt_peer_wait).  One CTA per peer.
+struct PushSeg {
+  const double* src;
+  long long count, dst_off;
+};
+__global__ void __launch_bounds__(128) k_peer_push(PushSeg s0, PushSeg s1, PushSeg s2, double* const* __restrict__ peer_bufs,
+                                                   unsigned long long* const* __restrict__ peer_flags, int rank,
+                                                   const unsigned long long* __restrict__ epoch_ctr) {
+  const unsigned long long epoch = *epoch_ctr + 1;   // bumped by the k_peer_wait that follows in stream order
+  double* dst = peer_bufs[blockIdx.x];
+  const PushSeg segs[3] = {s0, s1, s2};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    for (long long k = threadIdx.x; k < segs[i].count; k += blockDim.x) dst[segs[i].dst_off + k] = segs[i].src[k];
+  __threadfence_system();   // this thread's stores are visible system-wide ...
+  __syncthreads();          // ... and so are every thread's, before the flag is raised
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* f = peer_flags[blockIdx.x] + rank;
+    *f = epoch;
+  }
+}
+__global__ void k_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr) {
+  const unsigned long long epoch = *epoch_ctr + 1;
+  const int r = first + (int)threadIdx.x;
+  if (r <= last) {
+    const volatile unsigned long long* f = flags + r;
+    while (*f < epoch) __nanosleep(32);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch_ctr = epoch;
+}
+
 void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
   k_ell_sum<0><<<(unsigned)B, 256, 0, st>>>(ell_part, M, ell_out);
 }
@@ -418,6 +451,25 @@ int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t b
   if (!ln) return PSQRT_EUNSUPPORTED;
   if (!A || !L || cols <= 0 || batch <= 0) return PSQRT_EINVAL;
   ln->tria(A, L, cols, batch, (cudaStream_t)stream);
+  return check_launch();
+}
+
+int psqrt_peer_push(const double* src0, int64_t count0, int64_t dst_off0, const double* src1, int64_t count1,
+                    int64_t dst_off1, const double* src2, int64_t count2, int64_t dst_off2,
+                    double* const* peer_bufs, unsigned long long* const* peer_flags, int rank, int n_ranks,
+                    const unsigned long long* epoch_ctr, void* stream) {
+  if (!peer_bufs || !peer_flags || !epoch_ctr || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return PSQRT_EINVAL;
+  if ((count0 > 0 && !src0) || (count1 > 0 && !src1) || (count2 > 0 && !src2)) return PSQRT_EINVAL;
+  psq::PushSeg a{src0, count0, dst_off0}, b{src1, count1, dst_off1}, c{src2, count2, dst_off2};
+  psq::k_peer_push<<<n_ranks, 128, 0, (cudaStream_t)stream>>>(a, b, c, peer_bufs, peer_flags, rank, epoch_ctr);
+  return check_launch();
+}
+
+int psqrt_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr,
+                    void* stream) {
+  if (!flags || !epoch_ctr || first < 0 || last - first + 1 > 1024) return PSQRT_EINVAL;
+  const int n = last >= first ? last - first + 1 : 1;   // always launched: it also advances the epoch
+  psq::k_peer_wait<<<1, n, 0, (cudaStream_t)stream>>>(flags, first, last, epoch_ctr);
   return check_launch();
 }
 

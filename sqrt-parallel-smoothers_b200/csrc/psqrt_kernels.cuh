@@ -216,6 +216,7 @@ struct WarpOut {
   static constexpr int RECP = (VEC == 2) ? (((REC / 2) % 2 == 1) ? REC : REC + 2) : ((REC % 2 == 1) ? REC : REC + 1);
   static constexpr size_t smem_bytes(int threads) { return (size_t)threads * RECP * sizeof(double); }
   double* tile;   // this warp's [32][RECP]
+  unsigned tile_s;  // its shared-space address
   double *gm, *gL;
   long long c0;   // first chunk of the warp
   long long T;
@@ -223,20 +224,35 @@ struct WarpOut {
   // lane t writes trajectory index (c0 + t) K + j at step j, provided (c0 + t) K + j + voff < T
   __device__ __forceinline__ WarpOut(unsigned char* smem, double* m, double* L, long long c, int K_, long long T_, int voff_)
       : tile(reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x & ~31) * RECP), gm(m), gL(L),
-        c0(c - (threadIdx.x & 31)), T(T_), K(K_), voff(voff_), lane(threadIdx.x & 31) {}
+        c0(c - (threadIdx.x & 31)), T(T_), K(K_), voff(voff_), lane(threadIdx.x & 31) {
+    tile_s = (unsigned)__cvta_generic_to_shared(tile);
+  }
 
-  template <int W, int PER>   // W doubles per word, PER words per record; src offset in the tile record, dst array
-  __device__ __forceinline__ void copy_part(int j, int src_off, double* g) const {
+  // Copy one part (means or factors) of the tile out: W doubles per word, PER words per record.  Word e of the
+  // part (e = 32 i + lane) belongs to lane t = e / PER; because the lanes' chunks are consecutive, its global
+  // word address is linear in (e, t): B + e + t (K - 1) PER, and so is its address in the padded tile.
+  template <int W, int PER>
+  __device__ __forceinline__ void copy_part(int j, int nvalid, int src_off, double* g) const {
+    const long long B = (c0 * K + j) * PER;
+    const long long S = (long long)(K - 1) * PER;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {   // 32 * PER words in the tile, 32 per iteration
       const int e = i * 32 + lane;
-      const int t = e / PER, o = e - t * PER;
-      const long long k0 = (c0 + t) * K;
-      if (k0 + j + voff < T) {   // lane t has a record at this step
-        const double* sp = tile + t * RECP + src_off + o * W;
-        double* gp = g + (k0 + j) * (long long)(PER * W) + o * W;
-        if (W == 2) *reinterpret_cast<double2*>(gp) = *reinterpret_cast<const double2*>(sp);
-        else *gp = *sp;
+      const int t = e / PER;
+      // explicit PTX: an unconditional shared load (always inside the tile) and ONE predicated global store per
+      // word; left to the compiler this became a branch around every word with the address arithmetic redone
+      const unsigned sa = tile_s + (unsigned)((e + src_off / W + t * (RECP / W - PER)) * W * 8);
+      double* gp = g + (B + e + t * S) * W;
+      if (W == 2) {
+        double v0, v1;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(sa));
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %3, %4;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}"
+                     ::"l"(gp), "d"(v0), "d"(v1), "r"(t), "r"(nvalid) : "memory");
+      } else {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa));
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p st.global.f64 [%0], %1;\n\t}"
+                     ::"l"(gp), "d"(v), "r"(t), "r"(nvalid) : "memory");
       }
     }
   }
@@ -265,8 +281,10 @@ struct WarpOut {
       }
     }
     __syncwarp();
-    copy_part<VEC, N / VEC>(j, 0, gm);
-    copy_part<VEC, N * N / VEC>(j, N, gL);
+    // lanes with a record at this step form a prefix of the warp (their chunks are consecutive in time)
+    const int nvalid = __popc(__ballot_sync(kFull, (c0 + lane) * K + j + voff < T));
+    copy_part<VEC, N / VEC>(j, nvalid, 0, gm);
+    copy_part<VEC, N * N / VEC>(j, nvalid, N, gL);
     __syncwarp();
   }
 };

@@ -18,6 +18,8 @@
 #pragma once
 #include <math.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define PSQ_HD __host__ __device__ __forceinline__
 #define PSQ_UNROLL _Pragma("unroll")
@@ -145,50 +147,56 @@ struct Gauss {  // (mean, lower-triangular sqrt factor)
 // TRIBLK > 0 declares that row r has no non-zeros right of column TRIBLK + r (the second
 // block is itself lower triangular), which shortens every reflector.
 // ---------------------------------------------------------------------------------------
+// Compile-time loop: `#pragma unroll` is only a request, and for the larger blocks (N >= 5) nvcc left the row
+// loops of house_rows rolled, which turned the register matrices into local-memory arrays.
+template <int I, int E, class F>
+PSQ_HD void static_for(F&& f) {
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, E>(f);
+  }
+}
+
 template <int R, int C, int NREFL, int TRIBLK = 0>
 PSQ_HD void house_rows(double (&M)[R][C]) {
-  PSQ_UNROLL
-  for (int j = 0; j < NREFL; ++j) {
-    const int kend = (TRIBLK > 0) ? ((TRIBLK + j + 1 < C) ? TRIBLK + j + 1 : C) : C;
-    if (j + 1 >= kend) continue;
-    const double alpha = M[j][j];
-    // two partial sums halve the serial depth of the norm
-    double sigma = 0.0, sigma2 = 0.0;
-    PSQ_UNROLL
-    for (int k = j + 1; k < kend; k += 2) {
-      sigma = fma(M[j][k], M[j][k], sigma);
-      if (k + 1 < kend) sigma2 = fma(M[j][k + 1], M[j][k + 1], sigma2);
-    }
-    sigma += sigma2;
-    // Branch-free on purpose: a branch around the rsqrt / rcp chain stops the scheduler from
-    // overlapping it with the independent dot products below.  Only an all-zero row needs H = I
-    // (mask = 0, like dlarfg's tau = 0); a zero tail with alpha != 0 just flips the sign of column j.
-    const double q = fma(alpha, alpha, sigma);
-    const double mask = (q != 0.0) ? 1.0 : 0.0;
-    const double qs = (q != 0.0) ? q : 1.0;
-    const double norm = qs * rsqrt_nr(qs);
-    const double beta = -copysign(norm, alpha) * mask;
-    const double v0 = alpha - beta;  // = alpha + sign(alpha) * norm : no cancellation
-    const double s = rcp_nr(fma(fabs(alpha), norm, qs)) * mask;  // 1 / (norm (norm + |alpha|))
-    // the tail dot products do not depend on the norm: issued first so they overlap the
-    // rsqrt / rcp dependency chain; v0 and s enter last
-    double dots[(R - 1 > 0) ? R - 1 : 1];
-    PSQ_UNROLL
-    for (int i = j + 1; i < R; ++i) {
-      double d = 0.0;
+  static_for<0, NREFL>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    constexpr int kend = (TRIBLK > 0) ? ((TRIBLK + j + 1 < C) ? TRIBLK + j + 1 : C) : C;
+    if constexpr (j + 1 < kend) {
+      const double alpha = M[j][j];
+      // two partial sums halve the serial depth of the norm
+      double sigma = 0.0, sigma2 = 0.0;
       PSQ_UNROLL
-      for (int k = j + 1; k < kend; ++k) d = fma(M[i][k], M[j][k], d);
-      dots[i - 1] = d;
+      for (int k = j + 1; k < kend; k += 2) {
+        sigma = fma(M[j][k], M[j][k], sigma);
+        if (k + 1 < kend) sigma2 = fma(M[j][k + 1], M[j][k + 1], sigma2);
+      }
+      sigma += sigma2;
+      // Branch-free on purpose: a branch around the rsqrt / rcp chain stops the scheduler from
+      // overlapping it with the independent dot products below.  Only an all-zero row needs H = I
+      // (mask = 0, like dlarfg's tau = 0); a zero tail with alpha != 0 just flips the sign of column j.
+      const double q = fma(alpha, alpha, sigma);
+      const double mask = (q != 0.0) ? 1.0 : 0.0;
+      const double qs = (q != 0.0) ? q : 1.0;
+      const double norm = qs * rsqrt_nr(qs);
+      const double beta = -copysign(norm, alpha) * mask;
+      const double v0 = alpha - beta;  // = alpha + sign(alpha) * norm : no cancellation
+      const double s = rcp_nr(fma(fabs(alpha), norm, qs)) * mask;  // 1 / (norm (norm + |alpha|))
+      // the tail dot products do not depend on the norm: issued first so they overlap the
+      // rsqrt / rcp dependency chain; v0 and s enter last
+      static_for<j + 1, R>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        double d = 0.0;
+        PSQ_UNROLL
+        for (int k = j + 1; k < kend; ++k) d = fma(M[i][k], M[j][k], d);
+        d = fma(M[i][j], v0, d) * s;
+        M[i][j] = fma(-d, v0, M[i][j]);
+        PSQ_UNROLL
+        for (int k = j + 1; k < kend; ++k) M[i][k] = fma(-d, M[j][k], M[i][k]);
+      });
+      M[j][j] = beta;
     }
-    PSQ_UNROLL
-    for (int i = j + 1; i < R; ++i) {
-      const double d = fma(M[i][j], v0, dots[i - 1]) * s;
-      M[i][j] = fma(-d, v0, M[i][j]);
-      PSQ_UNROLL
-      for (int k = j + 1; k < kend; ++k) M[i][k] = fma(-d, M[j][k], M[i][k]);
-    }
-    M[j][j] = beta;
-  }
+  });
 }
 
 // Rank-K "update" tria([L | W]) with L (N x N) already lower triangular: row j's reflector

@@ -42,7 +42,7 @@ EXPORTS = (
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
-    "psqrt_fp64_probe",
+    "psqrt_fp64_probe", "psqrt_peer_push", "psqrt_peer_wait",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -318,6 +318,28 @@ def smoother_apply(ssm, fm, fL, carry_m, carry_L, *, write_terminal=True, chunk_
                                       ctypes.c_size_t(ws.numel()), _stream())
     _check(rc, "psqrt_smoother_apply")
     return sm, sL
+
+
+def peer_push(segments, peer_bufs: torch.Tensor, peer_flags: torch.Tensor, rank: int, n_ranks: int, epoch_ctr_ptr: int):
+    """psqrt_peer_push: segments = up to three (src tensor, destination offset in doubles); peer_bufs / peer_flags are
+    int64 DEVICE tensors holding the n_ranks peer base pointers; epoch_ctr_ptr: device address of the epoch word."""
+    lib = load()
+    segs = list(segments) + [(None, 0)] * (3 - len(segments))
+    args = []
+    for src, off in segs:
+        args += [_ptr(src), ctypes.c_int64(0 if src is None else src.numel()), ctypes.c_int64(off)]
+    with torch.cuda.device(peer_bufs.device):
+        rc = lib.psqrt_peer_push(*args, ctypes.c_void_p(peer_bufs.data_ptr()), ctypes.c_void_p(peer_flags.data_ptr()),
+                                 int(rank), int(n_ranks), ctypes.c_void_p(epoch_ctr_ptr), _stream())
+    _check(rc, "psqrt_peer_push")
+
+
+def peer_wait(flags_ptr: int, first: int, last: int, epoch_ctr_ptr: int, device):
+    lib = load()
+    with torch.cuda.device(device):
+        rc = lib.psqrt_peer_wait(ctypes.c_void_p(flags_ptr), int(first), int(last), ctypes.c_void_p(epoch_ctr_ptr),
+                                 _stream())
+    _check(rc, "psqrt_peer_wait")
 
 
 # ---- element-level seams ------------------------------------------------------------------------

@@ -52,15 +52,98 @@ def _all_gather(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out.view((world,) + tuple(x.shape))
 
 
-class TimeShardedSmoother:
-    """One filter + smoother pass over a sequence time-sharded across the ranks of `group`."""
+class PeerExchange:
+    """The two exchanges of a time-sharded pass over peer-mapped memory instead of NCCL.
 
-    def __init__(self, nx: int, ny: int, T_local: int, device=None, group=None, ops=None, chunk_len: int = 0):
+    Every rank owns one exchange buffer (torch symmetric memory: CUDA IPC / fabric handles, mapped into every
+    peer of the node).  A rank stores its shard total straight into slot `rank` of EVERY peer's buffer over
+    NVLink and raises that peer's flag (psqrt_peer_push); the consumer spins on its local flags in stream order
+    (psqrt_peer_wait) and the carry kernels read the totals from local memory.  No collective call, no host
+    synchronisation, no per-pass host argument (flags are monotonic epochs counted on the device), so a whole
+    pass can be captured in a CUDA graph.
+
+    A slot is rewritten only after its readers are done: rank a can push the totals of pass p + 1 only after its
+    own pass p finished, i.e. after it consumed what every reader b of that slot pushed LATER in pass p than b's
+    read of the slot (filter totals are read before the smoother push, smoother totals before the next pass's
+    filter push).
+
+    Layout (doubles): [2][R] flag words (filter, smoother) | 2 epoch words | F [R][B nf_f] | S [R][B nf_s] |
+    M [R][B nx] | L [R][B nx^2]."""
+
+    def __init__(self, world, rank, B, nf_f, nf_s, nx, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        R = world
+        self.R, self.rank, self.B, self.nx, self.nf_f, self.nf_s = R, rank, B, nx, nf_f, nf_s
+        self.sizes = (B * nf_f, B * nf_s, B * nx, B * nx * nx)
+        self.head = 2 * R + 2
+        n = self.head + R * sum(self.sizes)
+        grp = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.peer_flags = [torch.tensor([p + 8 * R * ph for p in ptrs], dtype=torch.int64, device=device) for ph in (0, 1)]
+        self.flags_ptr = [self.buf.data_ptr() + 8 * R * ph for ph in (0, 1)]
+        self.epoch_ptr = [self.buf.data_ptr() + 8 * (2 * R + ph) for ph in (0, 1)]
+        self.device = device
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every buffer is zeroed before anyone pushes
+
+    def _region(self, which):
+        """(offset of the region in doubles, slot size)"""
+        return self.head + self.R * sum(self.sizes[:which]), self.sizes[which]
+
+    def _view(self, which, shape):
+        off, slot = self._region(which)
+        return self.buf[off:off + self.R * slot].view((self.R,) + shape)
+
+    def exchange_filter(self, ops, ftotal):
+        """-> totals [R, B, nf_f]; entries of ranks < rank are valid when the returned view is read in stream order."""
+        off, slot = self._region(0)
+        ops.peer_push([(ftotal.contiguous(), off + self.rank * slot)], self.peer_bufs, self.peer_flags[0], self.rank,
+                      self.R, self.epoch_ptr[0])
+        ops.peer_wait(self.flags_ptr[0], 0, self.rank - 1, self.epoch_ptr[0], self.device)
+        return self._view(0, (self.B, self.nf_f))
+
+    def exchange_smoother(self, ops, stotal, m_last, L_last):
+        """-> (stotals [R, B, nf_s], mT [B, nx], LT [B, nx, nx] of the last rank)."""
+        R, r = self.R, self.rank
+        segs = []
+        for which, t in ((1, stotal), (2, m_last), (3, L_last)):
+            off, slot = self._region(which)
+            segs.append((t.contiguous(), off + r * slot))
+        ops.peer_push(segs, self.peer_bufs, self.peer_flags[1], r, R, self.epoch_ptr[1])
+        ops.peer_wait(self.flags_ptr[1], r + 1, R - 1, self.epoch_ptr[1], self.device)
+        return (self._view(1, (self.B, self.nf_s)), self._view(2, (self.B, self.nx))[R - 1],
+                self._view(3, (self.B, self.nx, self.nx))[R - 1])
+
+
+class TimeShardedSmoother:
+    """One filter + smoother pass over a sequence time-sharded across the ranks of `group`.
+
+    exchange = "peer": shard totals travel by P2P stores into peer-mapped buffers (PeerExchange; falls back to
+    NCCL if the symmetric-memory rendezvous is not available); "nccl": two all-gathers."""
+
+    def __init__(self, nx: int, ny: int, T_local: int, device=None, group=None, ops=None, chunk_len: int = 0,
+                 exchange: str = "nccl"):
         if ops is None:
             from . import _lib as ops
         self.ops, self.nx, self.ny, self.T, self.group, self.chunk_len = ops, nx, ny, T_local, group, chunk_len
         self.world, self.rank = _world(group)
         self.device = device
+        self.exchange = exchange if self.world > 1 else "nccl"
+        self._peer = None
+        self.exchange_error = None
+
+    def _peer_exchange(self, B, nf_f, nf_s):
+        if self._peer is None or self._peer.B != B:
+            try:
+                self._peer = PeerExchange(self.world, self.rank, B, nf_f, nf_s, self.nx, self.device, self.group)
+            except Exception as e:            # no symmetric memory on this system: NCCL all-gathers instead
+                self.exchange, self.exchange_error = "nccl", repr(e)
+                return None
+        return self._peer
 
     def filter_smoother(self, ssm, y, m0, L0, *, smooth: bool = True, loglik: bool = False):
         """ssm: psqrt._lib.LinearizedSSM of THIS shard; y [B, T_local, ny]; m0 [B, nx], L0 [B, nx, nx]
@@ -68,8 +151,16 @@ class TimeShardedSmoother:
         Returns (fm, fL, sm, sL, ell): local trajectories [B, T_local + 1, ...]; ell is the
         log-likelihood of the WHOLE sequence (same value on every rank) or None."""
         ops, R, r = self.ops, self.world, self.rank
+        B = y.shape[0]
         ftotal = ops.filter_reduce(ssm, y, self.nx, chunk_len=self.chunk_len)                 # [B, nf_filter]
-        totals = _all_gather(ftotal, R, self.group)                                          # [R, B, nf]
+        peer = None
+        if self.exchange == "peer":
+            nf_s = (3 * self.nx * self.nx + 3 * self.nx) // 2
+            peer = self._peer_exchange(B, ftotal.shape[-1], nf_s)
+        if peer is not None:
+            totals = peer.exchange_filter(ops, ftotal)
+        else:
+            totals = _all_gather(ftotal, R, self.group)                                      # [R, B, nf]
         cm, cL = ops.carry_filter(totals, r, m0.contiguous(), L0.contiguous())
         fm, fL, ell, stotal = ops.filter_apply(ssm, y, cm, cL, smooth=smooth, loglik=loglik,
                                                chunk_len=self.chunk_len)
@@ -77,13 +168,15 @@ class TimeShardedSmoother:
             dist.all_reduce(ell, op=dist.ReduceOp.SUM, group=self.group)
         if not smooth:
             return fm, fL, None, None, ell
-        B = y.shape[0]
         nfs = stotal.shape[-1]
-        payload = torch.cat([stotal, fm[:, -1], fL[:, -1].reshape(B, -1)], dim=-1)           # [B, nfs + nx + nx^2]
-        gathered = _all_gather(payload, R, self.group)
-        stotals = gathered[:, :, :nfs].contiguous()
-        mT = gathered[R - 1, :, nfs:nfs + self.nx].contiguous()
-        LT = gathered[R - 1, :, nfs + self.nx:].reshape(B, self.nx, self.nx).contiguous()
+        if peer is not None:
+            stotals, mT, LT = peer.exchange_smoother(ops, stotal, fm[:, -1], fL[:, -1])
+        else:
+            payload = torch.cat([stotal, fm[:, -1], fL[:, -1].reshape(B, -1)], dim=-1)       # [B, nfs + nx + nx^2]
+            gathered = _all_gather(payload, R, self.group)
+            stotals = gathered[:, :, :nfs].contiguous()
+            mT = gathered[R - 1, :, nfs:nfs + self.nx].contiguous()
+            LT = gathered[R - 1, :, nfs + self.nx:].reshape(B, self.nx, self.nx).contiguous()
         sm_c, sL_c = ops.carry_smoother(stotals, r, R, mT, LT)
         sm, sL = ops.smoother_apply(ssm, fm, fL, sm_c, sL_c, write_terminal=True, chunk_len=self.chunk_len)
         return fm, fL, sm, sL, ell
