@@ -12,5 +12,6 @@ Differences from the reference, by design:
 from ._extended import linearize as extended
 from ._cubature import linearize as cubature
 from ._gh import linearize as gauss_hermite
+from ._unscented import linearize as unscented
 
-__all__ = ["extended", "cubature", "gauss_hermite"]
+__all__ = ["extended", "cubature", "gauss_hermite", "unscented"]

@@ -46,7 +46,11 @@ def test_library_loaded_from_tree():
 @pytest.mark.parametrize("n,ny,T,K", [(4, 2, 1000, 0), (4, 2, 1000, 7), (4, 2, 1000, 1), (5, 2, 333, 4), (1, 1, 100, 3),
                                       (1, 3, 50, 2), (2, 3, 77, 5), (3, 3, 500, 16), (4, 2, 5, 2), (2, 1, 1, 1),
                                       (6, 4, 257, 3), (8, 4, 130, 0), (3, 1, 31, 1), (3, 1, 32, 1), (3, 1, 33, 1),
-                                      (4, 2, 4097, 1), (4, 2, 12289, 3)])
+                                      (4, 2, 4097, 1), (4, 2, 12289, 3),
+                                      # several groups in the mid scans (half-warp combines, psqrt_coop.cuh);
+                                      # T = 40000, K = 1: 40 groups, i.e. two group totals per half-warp at level C
+                                      (5, 2, 3000, 1), (3, 3, 2500, 1), (2, 1, 2100, 1), (1, 1, 1500, 1),
+                                      (4, 2, 40000, 1), (5, 2, 35000, 1)])
 def test_pass_vs_oracle_lgssm(n, ny, T, K):
     """Whole filter + smoother pass + ell on a time-invariant LGSSM, every chunk length regime
     (ragged tails, single chunk, > 1 CTA, > 32 warps in the mid scan)."""
@@ -300,7 +304,7 @@ def _torch_models(case):
 
 
 @pytest.mark.parametrize("dim_x,dim_y", [(1, 1), (2, 1), (3, 2), (2, 3), (4, 2)])
-@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite", "unscented"])
 def test_methods_api_lgssm(dim_x, dim_y, lin_name):
     """methods.filtering / smoothing / filter_smoother / iterated_smoothing through the public API,
     mirroring tests/test_parallel_filter.py:80-122, test_parallel_smoother.py:61-99 and
@@ -339,7 +343,7 @@ def test_methods_api_lgssm(dim_x, dim_y, lin_name):
     assert abs(ell2.item() - oell2) <= TOL_ELL * abs(oell2)
 
 
-@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite", "unscented"])
 def test_builtin_linearization_kernels(lin_name):
     """psqrt_linearize_builtin (csrc/psqrt_models.cu) against the oracle's linearization
     (linearization/_extended.py, _sigma_points.py, _cubature.py, _gh.py) at random nominal points,
@@ -417,7 +421,7 @@ def _bearings_setup(T, seed=0):
     return ys, m0, cholQ, cholR, (obs_f, trans_f), (oobs, otrans)
 
 
-@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite"])
+@pytest.mark.parametrize("lin_name", ["extended", "cubature", "gauss_hermite", "unscented"])
 def test_bearings_iterated_smoother(lin_name):
     """Config 2/3 shape at test size: coordinated-turn + 2 bearings, nx=5, iterated sqrt parallel
     smoother from the notebooks' initial nominal, 10 iterations, + log-likelihood."""

@@ -186,3 +186,59 @@ def test_reference_source_vectors():
         pytest.skip("tests/golden/reference_vectors.npz not generated")
     from golden.check_vectors import check_all
     check_all(path)
+
+
+# ---- SURVEY 8(f) components: unscented linearization, pathwise sampler --------------------------------
+def _next_vectors():
+    return np.load(os.path.join(GOLD, "reference_vectors_next.npz"))
+
+
+def test_unscented_vs_reference_source():
+    """oracle unscented == the reference's own parsmooth/linearization/_unscented.py run on the NumPy shim
+    (tests/golden/make_golden_next.py): weights, functional (bearings) and conditional (population) models,
+    and a whole LGSSM pass."""
+    z = _next_vectors()
+    for n in (1, 2, 5):
+        wm, wc, _ = O.unscented_weights(n)
+        np.testing.assert_allclose(wm, z[f"ut{n}_wm"], rtol=0, atol=1e-16)
+        np.testing.assert_allclose(wc, z[f"ut{n}_wc"], rtol=0, atol=1e-16)
+    Q, R, obs, trans = O.bearings_make_parameters(0.01, 0.1, 0.5, 0.01, np.array([-1.5, 0.5]), np.array([1.0, 1.0]))
+    tm = O.FunctionalModel(trans, O.MVNSqrt(np.zeros(5), np.linalg.cholesky(Q)))
+    om = O.FunctionalModel(obs, O.MVNSqrt(np.zeros(2), np.linalg.cholesky(R)))
+    x = O.MVNSqrt(z["bear_pts_m"], z["bear_pts_L"])
+    for name, model in (("t", tm), ("o", om)):
+        F, ch, b = O.unscented(model, x)
+        assert rel_err(F, z[f"bear_ut_{name}_F"]) < 1e-12 and rel_err(b, z[f"bear_ut_{name}_b"]) < 1e-12
+        assert rel_err(LLt(ch), LLt(z[f"bear_ut_{name}_chol"])) < 1e-10
+    tmod, omod = O.population_model(10.0, np.array([[0.09]]))
+    xp = O.MVNSqrt(z["pop_pts_m"], z["pop_pts_L"])
+    for name, model in (("t", tmod), ("o", omod)):
+        F, ch, b = O.unscented(model, xp)
+        assert rel_err(F, z[f"pop_ut_{name}_F"]) < 1e-12 and rel_err(b, z[f"pop_ut_{name}_b"]) < 1e-12
+        assert rel_err(LLt(ch), LLt(z[f"pop_ut_{name}_chol"])) < 1e-10
+    ltm = O.FunctionalModel(O.lgssm_function(z["lg_F"]), O.MVNSqrt(z["lg_b"], z["lg_cQ"]))
+    lom = O.FunctionalModel(O.lgssm_function(z["lg_H"]), O.MVNSqrt(z["lg_c"], z["lg_cR"]))
+    nom = O.MVNSqrt(z["lg_nom_m"], np.repeat(np.eye(3)[None], 15, 0))
+    f, ell = O.filtering(z["lg_ys"], O.MVNSqrt(z["lg_m0"], z["lg_L0"]), ltm, lom, O.unscented, nom, True, True)
+    s = O.smoothing(ltm, f, O.unscented, nom, True)
+    assert rel_err(f.mean, z["lg_ut_fm"]) < 1e-10 and rel_err(LLt(f.chol), LLt(z["lg_ut_fc"])) < 1e-10
+    assert rel_err(s.mean, z["lg_ut_sm"]) < 1e-10 and rel_err(LLt(s.chol), LLt(z["lg_ut_sc"])) < 1e-10
+    assert abs(ell - z["lg_ut_ell"]) <= 1e-10 * abs(z["lg_ut_ell"])
+
+
+def test_sampler_vs_reference_source():
+    """oracle pathwise sampler == parsmooth/_pathwise_sampler.py (parallel and sequential) on the same normal
+    draws; parallel == sequential (the reference's tests/test_sampler.py compares both with the smoother)."""
+    z = _next_vectors()
+    ltm = O.FunctionalModel(O.lgssm_function(z["lg_F"]), O.MVNSqrt(z["lg_b"], z["lg_cQ"]))
+    f, s = O.MVNSqrt(z["smp_fm"], z["smp_fc"]), O.MVNSqrt(z["smp_sm"], z["smp_sc"])
+    for lname, lin in (("ext", O.extended), ("cub", O.cubature)):
+        a = O.par_sampling(z["smp_eps"], ltm, f, lin, s)
+        b = O.seq_sampling(z["smp_eps"], ltm, f, lin, s)
+        assert rel_err(a, z[f"smp_{lname}_par"]) < 1e-12 and rel_err(b, z[f"smp_{lname}_seq"]) < 1e-12
+        assert rel_err(a, b) < 1e-12
+    Q, _, _, trans = O.bearings_make_parameters(0.01, 0.1, 0.5, 0.01, np.array([-1.5, 0.5]), np.array([1.0, 1.0]))
+    tm = O.FunctionalModel(trans, O.MVNSqrt(np.zeros(5), np.linalg.cholesky(Q)))
+    fb, sb = O.MVNSqrt(z["smpb_fm"], z["smpb_fc"]), O.MVNSqrt(z["smpb_sm"], z["smpb_sc"])
+    a = O.par_sampling(z["smpb_eps"], tm, fb, O.extended, sb)
+    assert rel_err(a, z["smpb_ext_par"]) < 1e-12
