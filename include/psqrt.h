@@ -157,6 +157,17 @@ int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t b
 int psqrt_chol_update_batched(double* L, const double* V, int n, int k, double alpha, int64_t batch,
                               void* stream);
 
+/* ---- pathwise sampler (parsmooth/_pathwise_sampler.py:13-38,61-81,109-124) ----------------------
+ * Joint samples of the smoothing distribution.  (g, E, D) are the n_elements = T + 1 smoothing elements
+ * of psqrt_smoother_elements (which equal the sampler's (inc_m, gain, inc_L) and, last, (m_T, 0, L_T));
+ * eps [n_elements, n_samples, nx] are standard normal draws, eps[0] makes the last state and eps[t + 1]
+ * the increment of step t (same indexing as upstream, lines 71-79); samples [n_elements, n_samples, nx].
+ * D enters with its diagonal made non-negative (column signs of tria are arbitrary).  Workspace:
+ * psqrt_sampler_workspace_bytes. */
+size_t psqrt_sampler_workspace_bytes(int nx, int64_t n_elements, int64_t n_samples);
+int psqrt_sample_paths(const double* g, const double* E, const double* D, const double* eps, double* samples,
+                       int nx, int64_t n_elements, int64_t n_samples, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- linearization of the built-in models as device code (one thread per time step) -----------
  * Replaces vmap(linearization_method(model, nominal)) of parallel/_filtering.py:110-119 and
  * _smoothing.py:50-55 for the models of the reference's tests / notebooks:

@@ -3,8 +3,8 @@
     python sqrt-parallel-smoothers_b200/build.py [--force] [--jobs J]
 
 One translation unit per state dimension nx (psqrt_inst.cu with -DPSQ_N=nx) so the fully
-unrolled templates compile in parallel; objects are cached under build/ keyed by the hash of
-the sources and flags.  The result is sqrt-parallel-smoothers_b200/psqrt/libpsqrt.so, which is
+unrolled templates compile in parallel; objects are cached under build/, each keyed by the hash of
+its own source, the headers it includes and the flags, so a change rebuilds only what depends on it.  The result is sqrt-parallel-smoothers_b200/psqrt/libpsqrt.so, which is
 git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 from __future__ import annotations
@@ -13,6 +13,7 @@ import argparse
 import concurrent.futures as cf
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -28,6 +29,7 @@ ALL_NX = (1, 2, 3, 4, 5, 6, 8)    # state dimensions the dispatcher knows (psqrt
 # report PSQRT_EUNSUPPORTED at run time)
 NX_LIST = tuple(int(v) for v in os.environ.get("PSQRT_NX_LIST", "").split(",") if v) or ALL_NX
 MAX_NY = 4                        # observation dimensions 1..MAX_NY for each of them
+_INC = re.compile(r'\s*#\s*include\s*"([^"]+)"')
 
 EXTRA = [f for f in os.environ.get("PSQRT_NVCC_EXTRA", "").split() if f]
 OUT = os.environ.get("PSQRT_OUT", OUT)
@@ -44,16 +46,33 @@ def _nvcc() -> str:
     return nvcc
 
 
-def _digest(extra: str) -> str:
+def _closure(src: str, seen=None) -> list:
+    """`src` and every file it #include "..."s, transitively (csrc/ and include/)."""
+    seen = seen if seen is not None else []
+    if src in seen or not os.path.isfile(src):
+        return seen
+    seen.append(src)
+    with open(src, "r") as f:
+        for line in f:
+            m = _INC.match(line)
+            if not m:
+                continue
+            name = m.group(1)
+            for base in (os.path.dirname(src), INCLUDE):
+                cand = os.path.normpath(os.path.join(base, name))
+                if os.path.isfile(cand):
+                    _closure(cand, seen)
+                    break
+    return seen
+
+
+def _digest(src: str, extra: str) -> str:
+    """Hash of one translation unit: its source, the headers it includes, the flags."""
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)):
-        if not os.path.isfile(os.path.join(CSRC, name)):
-            continue
-        with open(os.path.join(CSRC, name), "rb") as f:
-            h.update(name.encode())
+    for path in sorted(_closure(src)):
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode())
             h.update(f.read())
-    with open(os.path.join(INCLUDE, "psqrt.h"), "rb") as f:
-        h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(extra.encode())
     return h.hexdigest()[:16]
@@ -70,21 +89,23 @@ def _compile(args):
 
 def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
-    tag = _digest(f"{NX_LIST}{MAX_NY}")
+    units = []
+    inst = os.path.join(CSRC, "psqrt_inst.cu")
+    for n in ALL_NX:
+        defs = [f"-DPSQ_N={n}", f"-DPSQ_MAX_NY={MAX_NY}"]
+        if n not in NX_LIST:
+            defs.append("-DPSQ_STUB")       # launch table symbol only, no kernels
+        units.append((inst, os.path.join(BUILD, f"inst_n{n}_{_digest(inst, ' '.join(defs))}.o"), defs))
+    for name in ("psqrt_capi.cu", "psqrt_models.cu", "psqrt_sampler.cu"):
+        src = os.path.join(CSRC, name)
+        if os.path.exists(src):
+            units.append((src, os.path.join(BUILD, f"{name[6:-3]}_{_digest(src, '')}.o"), []))
+    tag = hashlib.sha256(" ".join(os.path.basename(u[1]) for u in units).encode()).hexdigest()[:16]
     stamp = OUT + ".stamp"
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == tag:
         if verbose:
             print(f"[psqrt build] up to date: {OUT}")
         return OUT
-    units = []
-    for n in ALL_NX:
-        defs = [f"-DPSQ_N={n}", f"-DPSQ_MAX_NY={MAX_NY}"]
-        if n not in NX_LIST:
-            defs.append("-DPSQ_STUB")       # launch table symbol only, no kernels
-        units.append((os.path.join(CSRC, "psqrt_inst.cu"), os.path.join(BUILD, f"inst_n{n}_{tag}.o"), defs))
-    units.append((os.path.join(CSRC, "psqrt_capi.cu"), os.path.join(BUILD, f"capi_{tag}.o"), []))
-    if os.path.exists(os.path.join(CSRC, "psqrt_models.cu")):
-        units.append((os.path.join(CSRC, "psqrt_models.cu"), os.path.join(BUILD, f"models_{tag}.o"), []))
     todo = [u for u in units if force or not os.path.exists(u[1])]
     jobs = jobs or min(len(todo), os.cpu_count() or 1) or 1
     if verbose:
@@ -101,8 +122,9 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
     with open(stamp, "w") as f:
         f.write(tag)
     # drop stale objects
+    keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(BUILD):
-        if name.endswith(".o") and tag not in name:
+        if name.endswith(".o") and name not in keep:
             os.remove(os.path.join(BUILD, name))
     if verbose:
         print(f"[psqrt build] wrote {OUT}")

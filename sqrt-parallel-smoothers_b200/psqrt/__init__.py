@@ -5,8 +5,8 @@ Drop-in for the ``sqrt=True, parallel=True`` path of EEA-sensors/sqrt-parallel-s
 the numerics run in hand-written sm_100a CUDA kernels (libpsqrt.so) behind a C ABI.
 """
 from ._base import MVNStandard, MVNSqrt, FunctionalModel, ConditionalMomentsModel, are_inputs_compatible
-from .methods import filtering, smoothing, filter_smoother, iterated_smoothing
+from .methods import filtering, smoothing, filter_smoother, iterated_smoothing, sampling
 from . import linearization, methods, models
 
 __all__ = ["MVNStandard", "MVNSqrt", "FunctionalModel", "ConditionalMomentsModel", "are_inputs_compatible",
-           "filtering", "smoothing", "filter_smoother", "iterated_smoothing", "linearization", "methods", "models"]
+           "filtering", "smoothing", "filter_smoother", "iterated_smoothing", "sampling", "linearization", "methods", "models"]

@@ -42,7 +42,7 @@ EXPORTS = (
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
-    "psqrt_fp64_probe", "psqrt_peer_push", "psqrt_peer_wait",
+    "psqrt_fp64_probe", "psqrt_peer_push", "psqrt_peer_wait", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -63,6 +63,8 @@ def load() -> ctypes.CDLL:
                          f"(or __graft_entry__.build()).  There is no CPU / eager fallback.")
     lib = ctypes.CDLL(_LIB_PATH)
     lib.psqrt_error_string.restype = ctypes.c_char_p
+    lib.psqrt_sampler_workspace_bytes.restype = ctypes.c_size_t
+    lib.psqrt_sampler_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int64]
     lib.psqrt_workspace_bytes.restype = ctypes.c_size_t
     lib.psqrt_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                           ctypes.c_int]
@@ -506,6 +508,27 @@ def chol_update_many(L: torch.Tensor, V: torch.Tensor, alpha: float) -> torch.Te
     Lb = Lb.reshape(*lead, n, n)
     Lb._psqrt_lower = True            # _utils.py:79: the update zeroes the upper triangle
     return Lb
+
+
+def sample_paths(g: torch.Tensor, E: torch.Tensor, D: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    """x_t = E_t x_{t+1} + g_t + D_t eps_t backwards through the n smoothing elements for every sample
+    (parsmooth/_pathwise_sampler.py:13-38): g [n, nx], E, D [n, nx, nx], eps [n, S, nx] -> samples [n, S, nx]."""
+    lib = load()
+    n_el, nx = g.shape
+    S = eps.shape[1]
+    assert E.shape == (n_el, nx, nx) and D.shape == (n_el, nx, nx) and eps.shape == (n_el, S, nx)
+    g, E, D, eps = (t.contiguous() for t in (g, E, D, eps))
+    out = torch.empty_like(eps)
+    nbytes = int(lib.psqrt_sampler_workspace_bytes(nx, ctypes.c_int64(n_el), ctypes.c_int64(S)))
+    if nbytes == 0:
+        raise PsqrtError(f"psqrt_sample_paths: unsupported sizes nx={nx}, n={n_el}, S={S}")
+    ws = workspace(nbytes, g.device)
+    with torch.cuda.device(g.device):
+        rc = lib.psqrt_sample_paths(_ptr(g), _ptr(E), _ptr(D), _ptr(eps), _ptr(out), nx, ctypes.c_int64(n_el),
+                                    ctypes.c_int64(S), ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()),
+                                    _stream())
+    _check(rc, "psqrt_sample_paths")
+    return out
 
 
 _points_cache = {}

@@ -184,6 +184,42 @@ def fixed_point(f, x0, criterion):
     return x
 
 
+def sampling(key, n_samples: int, transition_model, filter_trajectory, linearization_method: Callable,
+             nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True):
+    """parsmooth.methods.sampling (methods.py:79-91; _pathwise_sampler.py:13-38, 61-81, 109-124): joint samples
+    [T + 1, n_samples, nx] of the smoothing distribution given the filtered trajectory.
+
+    `key`: an int seed or a torch.Generator for the standard normal draws (upstream: a jax PRNGKey), or the draws
+    themselves as an array [T + 1, n_samples, nx] (draw 0 makes the last state, draw t + 1 the increment of step
+    t, as upstream).  The transition model is linearised at `nominal_trajectory` (default: the smoothed
+    trajectory, methods.py:86-87).  Each step's factor enters with a non-negative diagonal, so a given draw maps
+    to the same sample whatever sign convention the triangularisation used."""
+    _check_parallel(parallel)
+    dev = _device()
+    ft = _mvn(filter_trajectory, dev)
+    transition_model = _model(transition_model, dev)
+    T1, nx = ft.mean.shape
+    if nominal_trajectory is None:
+        nominal_trajectory = smoothing(transition_model, ft, linearization_method, None, parallel)
+    are_inputs_compatible(filter_trajectory, nominal_trajectory)
+    nominal = _mvn(nominal_trajectory, dev)
+    ssm = _linearize(linearization_method, transition_model, None, nominal)
+    fL = ft.chol
+    if bool((torch.triu(fL, 1) != 0).any()):      # kernels read lower triangles only
+        fL = _lib.tria(fL)
+    shape = (T1, int(n_samples), nx)
+    if isinstance(key, (np.ndarray, torch.Tensor)) and tuple(key.shape) == shape:
+        eps = _t(key, dev)
+    else:
+        gen = key
+        if not isinstance(gen, torch.Generator):
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(np.asarray(key).ravel()[-1]))
+        eps = torch.randn(shape, dtype=torch.float64, device=dev, generator=gen)
+    g, E, D = _lib.smoother_elements(ssm, ft.mean, fL)
+    return _lib.sample_paths(g, E, D, eps)
+
+
 def iterated_smoothing(observations, x0, transition_model, observation_model, linearization_method: Callable,
                        init_nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True,
                        criterion: Callable = _default_criterion, return_loglikelihood: bool = False):

@@ -545,6 +545,50 @@ def test_reference_golden_bearings():
     np.testing.assert_array_almost_equal(LLt(res.chol.cpu().numpy())[1:], exp_P, decimal=3)
 
 
+@pytest.mark.parametrize("n,ny,T,S", [(3, 2, 14, 6), (4, 2, 5000, 7), (1, 1, 300, 33), (5, 2, 2000, 130), (8, 4, 60, 5)])
+def test_sampler_vs_oracle(n, ny, T, S):
+    """psqrt.sampling (psqrt_smoother_elements + psqrt_sample_paths) against the oracle's restatement of
+    parsmooth/_pathwise_sampler.py on the SAME normal draws, in the sign convention of the CUDA path
+    (non-negative factor diagonals).  T = 5000 with 7 samples takes the time-chunked route, the others the
+    one-thread-per-sample route."""
+    import psqrt
+    case = lgssm_case(n, ny, T, seed=11 * n + ny)
+    tm, om = _torch_models(case)
+    otm, oom = oracle_lgssm_models(case)
+    x0 = psqrt.MVNSqrt(_g(case["m0"]), _g(case["L0"]))
+    filt = psqrt.filtering(case["ys"], x0, tm, om, psqrt.linearization.extended)
+    smo = psqrt.smoothing(tm, filt, psqrt.linearization.extended)
+    eps = np.random.RandomState(5).randn(T + 1, S, n)
+    got = psqrt.sampling(eps, S, tm, filt, psqrt.linearization.extended, smo)
+    of = O.MVNSqrt(filt.mean.cpu().numpy(), filt.chol.cpu().numpy())
+    os_ = O.MVNSqrt(smo.mean.cpu().numpy(), smo.chol.cpu().numpy())
+    exp = O.seq_sampling(eps, otm, of, O.extended, os_, canonical=True)
+    assert got.shape == (T + 1, S, n)
+    assert rel_err(got.cpu().numpy(), exp) < TOL
+    # nominal_trajectory=None linearises at the smoothed trajectory (methods.py:86-87): same result here
+    got2 = psqrt.sampling(eps, S, tm, filt, psqrt.linearization.extended)
+    assert rel_err(got2.cpu().numpy(), exp) < TOL
+
+
+@pytest.mark.parametrize("dim_x,dim_y", [(1, 2), (3, 3)])
+def test_sampler_marginals(dim_x, dim_y):
+    """The reference's own sampler test (tests/test_sampler.py:28-66): the marginals of 100 000 joint samples
+    reproduce the smoothing means and variances to 1e-2."""
+    import psqrt
+    T, N = 10, 100_000
+    case = lgssm_case(dim_x, dim_y, T, seed=3)
+    tm, om = _torch_models(case)
+    x0 = psqrt.MVNSqrt(_g(case["m0"]), _g(case["L0"]))
+    for lin in (psqrt.linearization.cubature, psqrt.linearization.extended):
+        filt = psqrt.filtering(case["ys"], x0, tm, om, lin)
+        smo = psqrt.smoothing(tm, filt, lin)
+        samples = psqrt.sampling(123, N, tm, filt, lin, smo)
+        assert samples.shape == (T + 1, N, dim_x)
+        var = LLt(smo.chol.cpu().numpy()).diagonal(axis1=1, axis2=2)
+        np.testing.assert_allclose(samples.mean(1).cpu().numpy(), smo.mean.cpu().numpy(), rtol=1e-2, atol=1e-2)
+        np.testing.assert_allclose(samples.var(1).cpu().numpy(), var, rtol=1e-2, atol=1e-2)
+
+
 def test_full_size_properties():
     """BASELINE size (T = 1e6, nx = 4) through size-independent properties: (1) the pass is
     invariant to the chunking (two different chunk lengths = two different association orders);

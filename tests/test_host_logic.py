@@ -140,5 +140,5 @@ def test_parsmooth_alias():
     from parsmooth._base import MVNSqrt
     import psqrt
     assert MVNSqrt is psqrt.MVNSqrt and parsmooth.methods is psqrt.methods
-    with pytest.raises(NotImplementedError):
-        parsmooth.sampling()
+    assert parsmooth.sampling is psqrt.methods.sampling
+    from parsmooth.linearization import unscented                          # noqa: F401

@@ -209,7 +209,11 @@ def test_unscented_vs_reference_source():
     for name, model in (("t", tm), ("o", om)):
         F, ch, b = O.unscented(model, x)
         assert rel_err(F, z[f"bear_ut_{name}_F"]) < 1e-12 and rel_err(b, z[f"bear_ut_{name}_b"]) < 1e-12
-        assert rel_err(LLt(ch), LLt(z[f"bear_ut_{name}_chol"])) < 1e-10
+        # Phi + Q - F P F^T is a difference of nearly equal matrices (_sigma_points.py:77-78): its error is
+        # measured on the scale of the terms
+        FL = F @ x.chol
+        scale = max(float(np.abs(LLt(ch)).max()), float(np.abs(LLt(FL)).max()))
+        assert float(np.abs(LLt(ch) - LLt(z[f"bear_ut_{name}_chol"])).max()) / scale < 1e-12
     tmod, omod = O.population_model(10.0, np.array([[0.09]]))
     xp = O.MVNSqrt(z["pop_pts_m"], z["pop_pts_L"])
     for name, model in (("t", tmod), ("o", omod)):
