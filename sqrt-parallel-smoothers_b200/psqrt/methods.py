@@ -18,7 +18,7 @@ from . import _lib
 from ._base import MVNSqrt, MVNStandard, FunctionalModel, ConditionalMomentsModel, are_inputs_compatible
 from ._lib import LinearizedSSM
 
-__all__ = ["filtering", "smoothing", "filter_smoother", "iterated_smoothing"]
+__all__ = ["filtering", "smoothing", "filter_smoother", "iterated_smoothing", "sampling"]
 
 
 def _device():
@@ -101,8 +101,17 @@ def _linearize(lin, transition_model, observation_model, nominal):
 
 def _prior_factor(L0):
     """The kernels read the lower triangle of the carry-in factor; any other square root of the
-    prior covariance is first triangularised (tria, parsmooth/_utils.py:22-24)."""
-    return _lib.tria(L0)
+    prior covariance is first triangularised (tria, parsmooth/_utils.py:22-24).  Memoised on the tensor
+    (with its version counter): an iterated smoother passes the same x0 every iteration."""
+    memo = getattr(L0, "_psqrt_prior", None)
+    if memo is not None and memo[0] == L0._version:
+        return memo[1]
+    out = _lib.tria(L0)
+    try:
+        L0._psqrt_prior = (L0._version, out)
+    except AttributeError:
+        pass
+    return out
 
 
 def _run(observations, x0, transition_model, observation_model, lin, nominal, smooth, loglik):
@@ -225,6 +234,12 @@ def iterated_smoothing(observations, x0, transition_model, observation_model, li
                        criterion: Callable = _default_criterion, return_loglikelihood: bool = False):
     """parsmooth.methods.iterated_smoothing (methods.py:54-76)."""
     _check_parallel(parallel)
+    # host inputs move to the device once, not once per iteration (each conversion is a blocking H2D copy)
+    dev = _device()
+    observations = _t(observations, dev)
+    x0 = _mvn(x0, dev)
+    transition_model = _model(transition_model, dev)
+    observation_model = _model(observation_model, dev)
     if init_nominal_trajectory is None:
         init_nominal_trajectory = filter_smoother(observations, x0, transition_model, observation_model,
                                                   linearization_method, None, parallel)
