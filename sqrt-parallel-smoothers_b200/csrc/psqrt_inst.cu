@@ -21,6 +21,10 @@ const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
 }
 #else
 #include "psqrt_kernels.cuh"
+#include "psqrt_coop.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace psq {
 namespace {
@@ -157,10 +161,30 @@ const LaunchNY* for_ny(int ny) {
 
 inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31) / 32), (unsigned)B, 1); }
 
+// The filtering mid-level scan runs one half-warp per combine (psqrt_coop.cuh) for nx >= 5, where the
+// one-thread-per-combine kernel spills; PSQRT_MID_SCAN=thread selects k_mid_scan everywhere (A/B timing).
+constexpr bool kCoopMid = (PSQ_N >= 5);
+inline bool use_coop_mid() {
+  static const bool on = [] {
+    const char* e = getenv("PSQRT_MID_SCAN");
+    return !(e && strcmp(e, "thread") == 0);
+  }();
+  return kCoopMid && on;
+}
 void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 cudaStream_t st) {
-  k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32 * Split<FElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, nullptr,
-                                                           nullptr);
+  if constexpr (kCoopMid) {
+    if (use_coop_mid()) {
+      constexpr size_t smem = coop_smem_bytes<N>();
+      static_assert(smem <= 227 * 1024, "cooperative mid scan: shared memory budget");
+      if (smem > 48 * 1024)  // per device, so not cached per process
+        cudaFuncSetAttribute(k_mid_scan_coop<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k_mid_scan_coop<N><<<mid_grid(M, B), 32 * kCoopWarps, smem, st>>>(items, M, groups, (M + 31) / 32, counter, total);
+      return;
+    }
+  }
+  k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32 * Split<FElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32,
+                                                                                 counter, total, nullptr, nullptr);
 }
 void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 const double* ell_part, double* ell_out, cudaStream_t st) {

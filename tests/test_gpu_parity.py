@@ -50,7 +50,8 @@ def test_library_loaded_from_tree():
                                       # several groups in the mid scans (half-warp combines, psqrt_coop.cuh);
                                       # T = 40000, K = 1: 40 groups, i.e. two group totals per half-warp at level C
                                       (5, 2, 3000, 1), (3, 3, 2500, 1), (2, 1, 2100, 1), (1, 1, 1500, 1),
-                                      (4, 2, 40000, 1), (5, 2, 35000, 1)])
+                                      (4, 2, 40000, 1), (5, 2, 35000, 1), (6, 4, 1100, 1), (8, 4, 1100, 1), (8, 4, 33000, 1),
+                                      (6, 3, 34000, 1)])
 def test_pass_vs_oracle_lgssm(n, ny, T, K):
     """Whole filter + smoother pass + ell on a time-invariant LGSSM, every chunk length regime
     (ragged tails, single chunk, > 1 CTA, > 32 warps in the mid scan)."""
