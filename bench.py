@@ -5,8 +5,9 @@
 
 Workload (BASELINE.json metric, SURVEY.md section 8d recipe C1 at the metric's length): random stable
 LGSSM, nx = 4, ny = 2, T = 1e6 per GPU, fp64, one `filter_smoother` pass = one step.  With N > 1
-(torchrun) the sequence is N x 1e6 steps long and time-sharded: local scans, two NCCL all-gathers of
-the shard totals, carry application (weak scaling).
+(torchrun) the sequence is N x 1e6 steps long and time-sharded: local scans, two exchanges of the
+shard totals (P2P stores into peer-mapped buffers, or NCCL all-gathers when peer mapping is unavailable),
+carry application (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM,
 `e2e` = the same pass through the public API with pinned HOST buffers (H2D of the observations and
@@ -444,9 +445,10 @@ def run_psqrt(args):
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C1 random stable LGSSM nx={NX} ny={NY}, T={T:.0e} steps per GPU, one sqrt parallel "
-                                   "filter_smoother pass per step" + (", time-sharded over the GPUs with 2 NCCL "
-                                                                      "all-gathers of shard totals" if world > 1 else ""),
+            "config": {"workload": f"random stable LGSSM (SURVEY 8d recipe C1) nx={NX} ny={NY}, T={T:.0e} steps per GPU, "
+                                   "one sqrt parallel filter_smoother pass per step"
+                                   + (", time-sharded over the GPUs with two exchanges of the shard totals (see "
+                                      "`exchange`)" if world > 1 else ""),
                        "nx": NX, "ny": NY, "T_per_gpu": T, "T_total": T * world, "chunk_len": plan.chunk_len,
                        "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
                        "launch": (graph_note if world > 1 else "eager launches"),
@@ -455,8 +457,10 @@ def run_psqrt(args):
                                      if sharded.exchange == "peer" else
                                      "NCCL all-gather x2" + (f" (peer exchange unavailable: {sharded.exchange_error})"
                                                              if sharded.exchange_error else ""))),
-                       "l2": "working set per pass (y 16 MB + filtered 160 MB + smoothed 160 MB) exceeds the 126 MB L2; "
-                             "no explicit flush"},
+                       "l2": (f"working set per pass per GPU (y {8e-6 * NY * T:.0f} MB + filtered "
+                              f"{8e-6 * (NX + NX * NX) * T:.0f} MB + smoothed {8e-6 * (NX + NX * NX) * T:.0f} MB) "
+                              + ("exceeds" if 8e-6 * (NY + 2 * (NX + NX * NX)) * T > 126 else "does NOT exceed")
+                              + " the 126 MB L2; no explicit flush")},
             "e2e": e2e, "gpu_launches": (5 if world == 1 else (11 if sharded.exchange == "peer" else 7)) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }

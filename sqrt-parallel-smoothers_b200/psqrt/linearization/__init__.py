@@ -9,9 +9,10 @@ Differences from the reference, by design:
   user-supplied torch function of a 1-D state and is differentiated with ``torch.func``;
 * only the square-root (``MVNSqrt``) branch exists -- ``MVNStandard`` raises NotImplementedError.
 """
+from ._common import get_conditional_model
 from ._extended import linearize as extended
 from ._cubature import linearize as cubature
 from ._gh import linearize as gauss_hermite
 from ._unscented import linearize as unscented
 
-__all__ = ["extended", "cubature", "gauss_hermite", "unscented"]
+__all__ = ["extended", "cubature", "gauss_hermite", "unscented", "get_conditional_model"]

@@ -116,6 +116,25 @@ def main():
     smp = sampling(key, 4, tm, fb, extended, sb, parallel=True)
     out["smpb_ext_par"], out["smpb_eps"] = A(smp), A(draws[0])
 
+    # 3. get_conditional_model (linearization/_common.py:17-66) on a function non-linear in x AND q ----------
+    from parsmooth.linearization import gauss_hermite, get_conditional_model
+    jnp = sys.modules["jax.numpy"]
+    for n in (1, 2):
+        a, bq, cc = rng.randn(n, n), rng.randn(n, n), rng.randn(n)
+        f = lambda x, q_, a=a, bq=bq, cc=cc: a @ x + jnp.sin(x) * q_ + bq @ q_ + 0.3 * q_ * q_ + cc   # noqa: E731
+        qmvn = MVNSqrt(rng.randn(n), 0.5 * tril(n))
+        xs_m, xs_L = rng.randn(3, n), np.stack([0.4 * tril(n) for _ in range(3)])
+        for k, v in dict(a=a, b=bq, c=cc, qm=qmvn.mean, qL=qmvn.chol, xm=xs_m, xL=xs_L).items():
+            out[f"gcm{n}_{k}"] = A(v)
+        # outer == inner for the sigma-point methods (as tests/test_linearization.py:243-284 does); inner extended
+        # under an outer cubature (the shim's complex-step jacfwd cannot be nested, so no extended-in-extended)
+        for tag, inner, outer in (("cub", cubature, cubature), ("gh", gauss_hermite, gauss_hermite),
+                                  ("ut", unscented, unscented), ("extcub", extended, cubature)):
+            model = get_conditional_model(f, qmvn, inner)
+            res = [outer(model, MVNSqrt(xs_m[i], xs_L[i])) for i in range(3)]
+            for j, nm in enumerate(("F", "chol", "b")):
+                out[f"gcm{n}_{tag}_{nm}"] = A(np.stack([A(r[j]) for r in res]))
+
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1024:.0f} KiB")
 

@@ -590,6 +590,44 @@ def test_sampler_marginals(dim_x, dim_y):
         np.testing.assert_allclose(samples.var(1).cpu().numpy(), var, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("n", [1, 2])
+def test_get_conditional_model(n):
+    """psqrt.linearization.get_conditional_model (linearization/_common.py:17-66) against the oracle on a function
+    that is non-linear in the state AND the noise, inner == outer for the sigma-point methods, inner extended under
+    an outer cubature, and the reference's linear check (tests/test_linearization.py:243-284) with extended in
+    extended; dimension mismatch raises NotImplementedError."""
+    import psqrt
+    from psqrt.linearization import get_conditional_model
+    from test_oracle_golden import _gcm_function
+    rng = np.random.RandomState(40 + n)
+    a, b, c = rng.randn(n, n), rng.randn(n, n), rng.randn(n)
+    at, bt, ct = _g(a), _g(b), _g(c)
+    f = lambda x, q: at @ x + torch.sin(x) * q + bt @ q + 0.3 * q * q + ct          # noqa: E731
+    of = _gcm_function(a, b, c)
+    qm, qL = rng.randn(n), 0.5 * (np.tril(rng.rand(n, n)) + np.eye(n))
+    T = 17
+    xm, xL = rng.randn(T, n), 0.4 * (np.tril(rng.rand(T, n, n)) + np.eye(n))
+    x, ox = psqrt.MVNSqrt(_g(xm), _g(xL)), O.MVNSqrt(xm, xL)
+    q, oq = psqrt.MVNSqrt(_g(qm), _g(qL)), O.MVNSqrt(qm, qL)
+    L = psqrt.linearization
+    for inner, outer in (("cubature", "cubature"), ("gauss_hermite", "gauss_hermite"), ("unscented", "unscented"),
+                         ("extended", "cubature"), ("extended", "extended")):
+        F, ch, rem = getattr(L, outer)(get_conditional_model(f, q, getattr(L, inner)), x)
+        oF, och, orem = getattr(O, outer)(O.get_conditional_model(of, oq, getattr(O, inner)), ox)
+        assert rel_err(F.cpu().numpy(), oF) < TOL and rel_err(rem.cpu().numpy(), orem) < TOL, (inner, outer)
+        assert rel_err(LLt(ch.cpu().numpy()), LLt(och)) < TOL, (inner, outer)
+    flin = lambda x, q: at @ x + bt @ q + ct                                        # noqa: E731
+    for name in ("extended", "cubature", "gauss_hermite", "unscented"):
+        F, ch, rem = getattr(L, name)(get_conditional_model(flin, q, getattr(L, name)), psqrt.MVNSqrt(_g(xm[0]), _g(xL[0])))
+        np.testing.assert_allclose(F.cpu().numpy(), a, atol=1e-8)
+        np.testing.assert_allclose(rem.cpu().numpy(), b @ qm + c, atol=1e-8)
+        np.testing.assert_allclose(LLt(ch.cpu().numpy()), LLt(b @ qL), atol=1e-8)
+    bad = _g(np.ones((n, n + 1)))
+    with pytest.raises(NotImplementedError):
+        get_conditional_model(lambda x, q: at @ x + bad @ q, psqrt.MVNSqrt(_g(np.zeros(n + 1)), _g(np.eye(n + 1))),
+                              L.extended)
+
+
 def test_full_size_properties():
     """BASELINE size (T = 1e6, nx = 4) through size-independent properties: (1) the pass is
     invariant to the chunking (two different chunk lengths = two different association orders);

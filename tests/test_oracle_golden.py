@@ -246,3 +246,46 @@ def test_sampler_vs_reference_source():
     fb, sb = O.MVNSqrt(z["smpb_fm"], z["smpb_fc"]), O.MVNSqrt(z["smpb_sm"], z["smpb_sc"])
     a = O.par_sampling(z["smpb_eps"], tm, fb, O.extended, sb)
     assert rel_err(a, z["smpb_ext_par"]) < 1e-12
+
+
+def _gcm_function(a, b, c):
+    """f(x, q) = a x + sin(x) q + b q + 0.3 q^2 + c (non-linear in both arguments), NumPy-batched, with partials."""
+    eye = np.eye(len(a))
+
+    def f(x, q):
+        return np.einsum("ij,...j->...i", a, x) + np.sin(x) * q + np.einsum("ij,...j->...i", b, q) + 0.3 * q * q + c
+
+    f.jac_q = lambda x, q: np.einsum("...i,ij->...ij", np.sin(x) + 0.6 * q, eye) + b
+    f.jac_x = lambda x, q: a + np.einsum("...i,ij->...ij", np.cos(x) * q, eye)
+    return f
+
+
+def test_get_conditional_model_vs_reference_source():
+    """oracle get_conditional_model == parsmooth/linearization/_common.py:17-66 run on the NumPy shim, for the
+    sigma-point methods (outer == inner, as tests/test_linearization.py:243-284) and inner extended under an outer
+    cubature; dimension mismatch raises NotImplementedError like upstream."""
+    z = _next_vectors()
+    for n in (1, 2):
+        f = _gcm_function(z[f"gcm{n}_a"], z[f"gcm{n}_b"], z[f"gcm{n}_c"])
+        q = O.MVNSqrt(z[f"gcm{n}_qm"], z[f"gcm{n}_qL"])
+        x = O.MVNSqrt(z[f"gcm{n}_xm"], z[f"gcm{n}_xL"])
+        for tag, inner, outer in (("cub", O.cubature, O.cubature), ("gh", O.gauss_hermite, O.gauss_hermite),
+                                  ("ut", O.unscented, O.unscented), ("extcub", O.extended, O.cubature)):
+            F, ch, b = outer(O.get_conditional_model(f, q, inner), x)
+            assert rel_err(F, z[f"gcm{n}_{tag}_F"]) < 1e-12 and rel_err(b, z[f"gcm{n}_{tag}_b"]) < 1e-12
+            assert rel_err(LLt(ch), LLt(z[f"gcm{n}_{tag}_chol"])) < 1e-12
+    # the reference's own check on a linear f (tests/test_linearization.py:243-284), extended in extended
+    rng = np.random.RandomState(0)
+    a, b, c = rng.randn(2, 2), rng.randn(2, 2), rng.randn(2)
+    f = lambda x, q: np.einsum("ij,...j->...i", a, x) + np.einsum("ij,...j->...i", b, q) + c      # noqa: E731
+    f.jac_q = lambda x, q: np.broadcast_to(b, x.shape[:-1] + b.shape)
+    f.jac_x = lambda x, q: np.broadcast_to(a, x.shape[:-1] + a.shape)
+    q = O.MVNSqrt(rng.randn(2), np.tril(rng.rand(2, 2)))
+    x = O.MVNSqrt(rng.randn(2), np.tril(rng.rand(2, 2)))
+    for lin in (O.extended, O.cubature):
+        F, ch, rem = lin(O.get_conditional_model(f, q, lin), x)
+        np.testing.assert_allclose(F, a, atol=1e-10)
+        np.testing.assert_allclose(rem, b @ q.mean + c, atol=1e-10)
+        np.testing.assert_allclose(LLt(ch), LLt(b @ q.chol), atol=1e-10)
+    with pytest.raises(NotImplementedError):
+        O.get_conditional_model(lambda x, q: a @ x + np.ones((2, 3)) @ q, O.MVNSqrt(np.zeros(3), np.eye(3)), O.extended)
