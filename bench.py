@@ -481,7 +481,9 @@ def run_bearings(args):
     dev = torch.device("cuda", 0)
     T = args.T if args.T != T_PER_GPU else 100_000
     s1, s2, r, dt, qc, qw = np.array([-1.5, 0.5]), np.array([1.0, 1.0]), 0.5, 0.01, 0.01, 0.1
-    _, _, ys = bearings.get_data(np.array([0.1, 0.2, 1.0, 0.0]), dt, r, T, s1, s2, random_state=0)
+    runs = max(args.runs, 1)      # > 1: BASELINE.json configs[4], independent Monte-Carlo runs one after the other
+    ys_all = [bearings.get_data(np.array([0.1, 0.2, 1.0, 0.0]), dt, r, T, s1, s2, random_state=k)[2] for k in range(runs)]
+    ys = ys_all[0]
     Q, R, obs_f, trans_f = bearings.make_parameters(qc, qw, r, dt, s1, s2)
     g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
     x0 = psqrt.MVNSqrt(np.array([-4.0, -1.0, 2.0, 7.0, 3.0]), np.eye(5))
@@ -489,12 +491,20 @@ def run_bearings(args):
     om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(np.zeros(2), np.linalg.cholesky(R)))
     nominal = psqrt.MVNSqrt(g(np.tile(np.array([-1.0, -1.0, 6.0, 4.0, 2.0]), (T + 1, 1))),
                             torch.eye(5, dtype=torch.float64, device=dev).expand(T + 1, 5, 5))
-    ys_d = g(ys.astype(np.float64))
+    ys_ds = [g(y.astype(np.float64)) for y in ys_all]
     lin = getattr(psqrt.linearization, args.lin)
-    n_iter = 10
+    n_iter = args.iters
+
+    ys_batch = torch.stack(ys_ds) if args.batched else None
 
     def run():
-        return psqrt.iterated_smoothing(ys_d, x0, tm, om, lin, nominal, True, criterion=lambda i, *_: i < n_iter)
+        if args.batched:     # all runs in ONE pass per iteration (batch axis of the kernels)
+            from psqrt.dist import iterated_smoothing_batched
+            return iterated_smoothing_batched(ys_batch, x0, tm, om, lin, nominal, n_iter=n_iter)
+        res = None
+        for ys_d in ys_ds:
+            res = psqrt.iterated_smoothing(ys_d, x0, tm, om, lin, nominal, True, criterion=lambda i, *_: i < n_iter)
+        return res
 
     for _ in range(max(args.warmup, 2)):
         run()
@@ -507,8 +517,11 @@ def run_bearings(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     print(json.dumps({"workload": f"bearings-only CT nx=5 ny=2 T={T}, iterated sqrt {args.lin} parallel smoother, "
-                                  f"{n_iter} iterations (BASELINE.json configs[1])",
-                      "ms_per_call": ms, "value": T * n_iter / (ms * 1e-3), "unit": "step-passes/s",
+                                  f"{n_iter} iterations" + (f", {runs} independent runs "
+                                                            + ("as one batch" if args.batched else "in sequence")
+                                                            + " (BASELINE.json configs[4])" if runs > 1
+                                                            else " (BASELINE.json configs[1])"),
+                      "ms_per_call": ms, "value": runs * T * n_iter / (ms * 1e-3), "unit": "step-passes/s",
                       "finite": bool(torch.isfinite(res.mean).all().item())}))
     return 0
 
@@ -525,7 +538,10 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="chunk length override (0 = library default)")
     ap.add_argument("--workload", default="lgssm", choices=["lgssm", "bearings"],
                     help="lgssm = the driver's metric; bearings = informational configs[1] line")
-    ap.add_argument("--lin", default="extended", choices=["extended", "cubature", "gauss_hermite"])
+    ap.add_argument("--lin", default="extended", choices=["extended", "cubature", "gauss_hermite", "unscented"])
+    ap.add_argument("--runs", type=int, default=1, help="bearings workload: independent data sets smoothed in sequence")
+    ap.add_argument("--batched", action="store_true", help="bearings workload: smooth the runs as one batch")
+    ap.add_argument("--iters", type=int, default=10, help="bearings workload: iterations of the iterated smoother")
     ap.add_argument("--nx", type=int, default=4, help="state dimension of the LGSSM workload (informational runs; "
                                                       "the driver's metric is the default nx=4, ny=2)")
     ap.add_argument("--ny", type=int, default=2)

@@ -247,3 +247,79 @@ def iterated_smoothing_sharded(observations_local, x0: MVNSqrt, transition_model
         del filt
         return nominal, ell
     return nominal
+
+
+# ---------------------------------------------------------------------------------------------------
+# Batch of independent sequences (BASELINE.json configs[4]: Monte-Carlo runs).  The batch is the outermost
+# axis of every kernel (blockIdx.y), so B short sequences fill the GPU in ONE pass per iteration instead of B
+# latency-bound passes; across GPUs the runs are dealt round-robin (batch_indices) with no collective.
+# ---------------------------------------------------------------------------------------------------
+def _linearize_batched(lin, transition_model, observation_model, nominal: MVNSqrt):
+    """methods._linearize for a nominal trajectory with a leading batch axis [B, T + 1, ...]: transition at
+    nominal[:, :-1], observation at nominal[:, 1:] (parallel/_filtering.py:103-104, 117-119)."""
+    from . import methods
+    from ._lib import LinearizedSSM
+    F, cholQ, b = lin(transition_model, MVNSqrt(nominal.mean[:, :-1], nominal.chol[:, :-1]))
+    cholQ = methods._lower(cholQ)
+    H, cholR, c = lin(observation_model, MVNSqrt(nominal.mean[:, 1:], nominal.chol[:, 1:]))
+    return LinearizedSSM(F, cholQ, b, H, cholR, c)
+
+
+def filter_smoother_batched(observations, x0: MVNSqrt, transition_model, observation_model,
+                            linearization_method: Callable, nominal: Optional[MVNSqrt] = None,
+                            return_loglikelihood: bool = False):
+    """psqrt.methods.filter_smoother for B independent sequences at once: observations [B, T, ny], x0 shared
+    ([nx], [nx, nx]) or per sequence ([B, nx], [B, nx, nx]), nominal [B, T + 1, ...] (default: zeros / identity).
+    Returns (filtered, smoothed[, ell [B]]) with a leading batch axis; every sequence gets exactly what the
+    unbatched call returns for it."""
+    from . import _lib, methods
+    dev = methods._device()
+    ys = methods._t(observations, dev)
+    B, T, _ = ys.shape
+    x0 = methods._mvn(x0, dev)
+    nx = x0.mean.shape[-1]
+    transition_model = methods._model(transition_model, dev)
+    observation_model = methods._model(observation_model, dev)
+    if nominal is None:
+        mean = torch.zeros((B, T + 1, nx), dtype=torch.float64, device=dev)
+        nominal = MVNSqrt(mean, torch.eye(nx, dtype=torch.float64, device=dev).expand(B, T + 1, nx, nx))
+    else:
+        nominal = methods._mvn(nominal, dev)
+    ssm = _linearize_batched(linearization_method, transition_model, observation_model, nominal)
+    m0 = x0.mean.expand(B, nx).contiguous()
+    L0 = methods._prior_factor(x0.chol).expand(B, nx, nx).contiguous()
+    fm, fL, sm, sL, ell = _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=return_loglikelihood)
+    fm[:, 0].copy_(x0.mean.expand(B, nx))          # entry 0 is x0 itself (parallel/_filtering.py:45-46)
+    fL[:, 0].copy_(x0.chol.expand(B, nx, nx))
+    if return_loglikelihood:
+        return MVNSqrt(fm, fL), MVNSqrt(sm, sL), ell
+    return MVNSqrt(fm, fL), MVNSqrt(sm, sL)
+
+
+def iterated_smoothing_batched(observations, x0: MVNSqrt, transition_model, observation_model,
+                               linearization_method: Callable, init_nominal: Optional[MVNSqrt] = None,
+                               n_iter: int = 10, return_loglikelihood: bool = False):
+    """parsmooth.methods.iterated_smoothing (methods.py:54-76) with the fixed-count criterion
+    `lambda i, *_: i < n_iter` for B independent sequences at once (notebooks/robustness_100runs.py runs them one
+    after the other).  init_nominal: [B, T + 1, ...] or a single [T + 1, ...] trajectory shared by all sequences."""
+    from . import methods
+    dev = methods._device()
+    ys = methods._t(observations, dev)
+    B = ys.shape[0]
+    x0 = methods._mvn(x0, dev)
+    transition_model = methods._model(transition_model, dev)
+    observation_model = methods._model(observation_model, dev)
+    args = (ys, x0, transition_model, observation_model, linearization_method)
+    if init_nominal is None:
+        _, nominal = filter_smoother_batched(*args, None)
+    else:
+        nominal = methods._mvn(init_nominal, dev)
+        if nominal.mean.dim() == 2:
+            nominal = MVNSqrt(nominal.mean.expand(B, *nominal.mean.shape), nominal.chol.expand(B, *nominal.chol.shape))
+    # methods.fixed_point: one application, then again while criterion(i, ...) holds, i = 1, 2, ... -> n_iter in all
+    for _ in range(n_iter):
+        _, nominal = filter_smoother_batched(*args, nominal)
+    if return_loglikelihood:
+        _, _, ell = filter_smoother_batched(*args, nominal, True)
+        return nominal, ell
+    return nominal

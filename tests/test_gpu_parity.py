@@ -450,6 +450,44 @@ def test_bearings_iterated_smoother(lin_name):
     _check_traj("one pass at the oracle's nominal", one.mean, one.chol, oone.mean, oone.chol)
 
 
+@pytest.mark.parametrize("lin_name", ["extended", "cubature"])
+def test_bearings_batched_runs(lin_name):
+    """Config 5 shape at test size: independent bearings-only runs smoothed as ONE batch
+    (psqrt.dist.iterated_smoothing_batched) give, run by run, what psqrt.iterated_smoothing gives for each
+    run on its own (bit-identical kernels per sequence) and what the oracle gives for the first run."""
+    import psqrt
+    from psqrt.dist import iterated_smoothing_batched
+    T, B, n_iter = 300, 5, 4
+    sets = [_bearings_setup(T, seed=k) for k in range(B)]
+    ys, m0, cholQ, cholR, (obs_f, trans_f), (oobs, otrans) = sets[0]
+    lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+    x0 = psqrt.MVNSqrt(_g(m0), _g(np.eye(5)))
+    tm = psqrt.FunctionalModel(trans_f, psqrt.MVNSqrt(_g(np.zeros(5)), _g(cholQ)))
+    om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(_g(np.zeros(2)), _g(cholR)))
+    nom_m = np.tile(np.array([-1.0, -1.0, 6.0, 4.0, 2.0]), (T + 1, 1))
+    nom_L = np.repeat(np.eye(5)[None], T + 1, 0)
+    nominal = psqrt.MVNSqrt(_g(nom_m), _g(nom_L))
+    ys_b = np.stack([s_[0] for s_ in sets])
+    res, ell = iterated_smoothing_batched(ys_b, x0, tm, om, lin, nominal, n_iter=n_iter, return_loglikelihood=True)
+    assert res.mean.shape == (B, T + 1, 5) and ell.shape == (B,)
+    for k in range(B):
+        one, ell1 = psqrt.iterated_smoothing(sets[k][0], x0, tm, om, lin, nominal, True,
+                                             criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)
+        _check_traj(f"run {k}", res.mean[k], res.chol[k], one.mean.cpu().numpy(), one.chol.cpu().numpy(), tol=1e-12)
+        assert abs(ell[k].item() - ell1.item()) <= 1e-12 * abs(ell1.item())
+    otm = O.FunctionalModel(otrans, O.MVNSqrt(np.zeros(5), cholQ))
+    oom = O.FunctionalModel(oobs, O.MVNSqrt(np.zeros(2), cholR))
+    ores, oell = O.iterated_smoothing(ys, O.MVNSqrt(m0, np.eye(5)), otm, oom, olin, O.MVNSqrt(nom_m, nom_L), True,
+                                      criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)
+    _check_traj("run 0 vs oracle", res.mean[0], res.chol[0], ores.mean, ores.chol, tol=1e-8)
+    assert abs(ell[0].item() - oell) <= 1e-8 * abs(oell)
+    # default nominal (zeros / identity) and per-sequence priors
+    x0b = psqrt.MVNSqrt(_g(np.tile(m0, (B, 1))), _g(np.repeat(np.eye(5)[None], B, 0)))
+    res2 = iterated_smoothing_batched(ys_b, x0b, tm, om, lin, None, n_iter=2)
+    one2 = psqrt.iterated_smoothing(sets[1][0], x0, tm, om, lin, None, True, criterion=lambda i, *_: i < 2)
+    _check_traj("default nominal", res2.mean[1], res2.chol[1], one2.mean.cpu().numpy(), one2.chol.cpu().numpy(), tol=1e-12)
+
+
 def test_population_model():
     """Config 5b: Ricker / Poisson conditional-moments model, nx = ny = 1, sqrt path
     (notebooks/population_model.py; experiment-poisson.ipynb: lam = 10, Q = 0.09, x0 = log 7)."""
