@@ -9,9 +9,9 @@
 // (associative_scan over 2 log2 T levels of [T, S, n] arrays).  Here samples are the parallel axis and
 // time is cut into P chunks only as far as the GPU needs more threads than S:
 //   k_sample_gprod   thread per chunk:            G_c = E_{k0} ... E_{k1-1}
-//   k_sample_reduce  thread per (chunk, sample):  e_c = the recursion through the chunk from x = 0
-//   k_sample_mid     thread per sample:           chunk-boundary states, x_c = G_c x_{c+1} + e_c (P steps)
-//   k_sample_apply   thread per (chunk, sample):  the recursion from the boundary state, samples written
+//   k_sample_sweep<false>  thread per (chunk, sample):  e_c = the recursion through the chunk from x = 0
+//   k_sample_mid           thread per sample:           chunk-boundary states, x_c = G_c x_{c+1} + e_c (P steps)
+//   k_sample_sweep<true>   thread per (chunk, sample):  the recursion from the boundary state, samples written
 // Consecutive threads are consecutive samples, so the draws eps[t, s, :] and the outputs are read and
 // written as contiguous 32 n-double runs per warp; E_t, g_t, D_t are warp-uniform (broadcast) loads.
 // The pass is HBM-bound: 8 n bytes of draws in (twice when P > 1) and 8 n bytes of samples out per
@@ -24,45 +24,20 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <type_traits>
+
 #include "psqrt.h"
 
 namespace psq {
 namespace {
 
-template <int N>
-struct StepCoef {   // E, g and sign-normalised D of one element, in registers (warp-uniform values)
-  double E[N][N], g[N], D[N][N];
-  __device__ __forceinline__ void load(const double* __restrict__ gp, const double* __restrict__ Ep,
-                                       const double* __restrict__ Dp, long long t) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = __ldg(gp + t * N + i);
-    double sg[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) sg[j] = (__ldg(Dp + t * N * N + j * N + j) < 0.0) ? -1.0 : 1.0;
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        E[i][j] = __ldg(Ep + t * N * N + i * N + j);
-        D[i][j] = (j <= i) ? __ldg(Dp + t * N * N + i * N + j) * sg[j] : 0.0;
-      }
+template <int I, int E, class F>
+__device__ __forceinline__ void static_for_s(F&& f) {   // compile-time loop: register arrays need static indices
+  if constexpr (I < E) {
+    f(std::integral_constant<int, I>{});
+    static_for_s<I + 1, E>(f);
   }
-  // x <- E x + g + D e
-  __device__ __forceinline__ void step(double (&x)[N], const double (&e)[N]) const {
-    double y[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double s = g[i];
-#pragma unroll
-      for (int j = 0; j < N; ++j) s = fma(E[i][j], x[j], s);
-#pragma unroll
-      for (int j = 0; j <= i; ++j) s = fma(D[i][j], e[j], s);
-      y[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = y[i];
-  }
-};
+}
 
 // draws of element t: eps[(t + 1) % n_el]  (eps[0] makes the last state, _pathwise_sampler.py:71,79)
 __device__ __forceinline__ long long eps_row(long long t, long long n_el) { return (t + 1 == n_el) ? 0 : t + 1; }
@@ -99,34 +74,109 @@ __global__ void k_sample_gprod(const double* __restrict__ E, long long n_el, int
     for (int j = 0; j < N; ++j) G[c * N * N + i * N + j] = A[i][j];
 }
 
-// APPLY = false: e_c (from x = 0) -> ebuf[c][s];  APPLY = true: from the boundary state xb[c + 1][s], writing samples
+// APPLY = false: e_c (from x = 0) -> ebuf[c][s];  APPLY = true: from the boundary state xb[c + 1][s], writing samples.
+// All 128 threads of a CTA work on the SAME chunk (consecutive samples), so the coefficients (g_t, E_t, sign-
+// normalised D_t) of a tile of kTile steps are staged once per CTA in shared memory -- fetched into registers while
+// the previous tile is being processed, so their latency is hidden -- and read back as broadcasts; each thread's
+// draws come through a 4-deep register ring (loads issued 4 steps ahead of their use).  ncu on the first version
+// (coefficients and draws loaded at the point of use): 18-24 warps per issue stalled on long_scoreboard.
+constexpr int kTile = 16;
+
 template <int N, bool APPLY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_sample_sweep(const double* __restrict__ g, const double* __restrict__ E, const double* __restrict__ D,
                const double* __restrict__ eps, long long n_el, long long S, int K, long long P,
                const double* __restrict__ xb, double* __restrict__ out) {
-  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int NN = N * N, NC = N + 2 * NN;          // per step: g [N], E [N][N], D [N][N]
+  constexpr int NV = (kTile * NC + 127) / 128;        // staged values per thread and tile
+  __shared__ double coef[kTile * NC];
+  const int tid = threadIdx.x;
+  const long long s = (long long)blockIdx.x * 128 + tid;
+  const bool live = s < S;                            // no early return: every thread stages and synchronises
   const long long c = blockIdx.y;
-  if (s >= S) return;
   const long long k0 = c * K, k1 = (k0 + K < n_el) ? k0 + K : n_el;
   double x[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) x[i] = (APPLY && c + 1 < P) ? xb[((c + 1) * S + s) * N + i] : 0.0;
-  for (long long t = k1 - 1; t >= k0; --t) {
-    StepCoef<N> co;
-    co.load(g, E, D, t);
-    const double* ep = eps + (eps_row(t, n_el) * S + s) * N;
-    double e[N];
+  for (int i = 0; i < N; ++i) x[i] = (APPLY && live && c + 1 < P) ? xb[((c + 1) * S + s) * N + i] : 0.0;
+
+  double sv[NV];
+  auto fetch = [&](long long hi) {                     // coefficients of steps hi, hi - 1, ... -> registers
 #pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = __ldcs(ep + i);   // streamed once per sweep
-    co.step(x, e);
-    if (APPLY) {
-      double* o = out + (t * S + s) * N;
-#pragma unroll
-      for (int i = 0; i < N; ++i) __stcs(o + i, x[i]);
+    for (int v = 0; v < NV; ++v) {
+      const int idx = tid + v * 128;
+      const int u = idx / NC, f = idx % NC;
+      const long long t = hi - u;
+      double val = 0.0;
+      if (idx < kTile * NC && t >= k0) {
+        if (f < N) {
+          val = __ldg(g + t * N + f);
+        } else if (f < N + NN) {
+          val = __ldg(E + t * NN + (f - N));
+        } else {
+          const int q = f - N - NN, i = q / N, j = q % N;
+          const double d = __ldg(D + t * NN + q), dj = __ldg(D + t * NN + j * N + j);
+          val = (j <= i) ? (dj < 0.0 ? -d : d) : 0.0;   // lower triangle, non-negative diagonal
+        }
+      }
+      sv[v] = val;
     }
+  };
+  double er[4][N];
+  auto eload = [&](auto slot, long long t) {
+    if (live && t >= k0) {
+      const double* ep = eps + (eps_row(t, n_el) * S + s) * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) er[decltype(slot)::value][i] = __ldcs(ep + i);   // streamed once per sweep
+    }
+  };
+  long long hi = k1 - 1;
+  fetch(hi);
+  eload(std::integral_constant<int, 0>{}, hi);
+  eload(std::integral_constant<int, 1>{}, hi - 1);
+  eload(std::integral_constant<int, 2>{}, hi - 2);
+  eload(std::integral_constant<int, 3>{}, hi - 3);
+#pragma unroll 1
+  while (hi >= k0) {
+    __syncthreads();                                   // the previous tile has been read by everyone
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (tid + v * 128 < kTile * NC) coef[tid + v * 128] = sv[v];
+    __syncthreads();
+    if (hi - kTile >= k0) fetch(hi - kTile);           // in flight during this tile's steps
+#pragma unroll 1
+    for (int u0 = 0; u0 < kTile; u0 += 4)              // rolled: registers stay low enough for ~16 warps per SM
+    static_for_s<0, 4>([&](auto uc) {
+      constexpr int slot = decltype(uc)::value;        // ring slot = step index mod 4 (kTile is a multiple of 4)
+      const int u = u0 + slot;
+      const long long t = hi - u;
+      if (t >= k0) {                                   // uniform over the CTA
+        double e[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[i] = er[slot][i];
+        eload(std::integral_constant<int, slot>{}, t - 4);
+        const double* cf = coef + u * NC;
+        double y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double a = cf[i];
+#pragma unroll
+          for (int j = 0; j < N; ++j) a = fma(cf[N + i * N + j], x[j], a);
+#pragma unroll
+          for (int j = 0; j <= i; ++j) a = fma(cf[N + NN + i * N + j], e[j], a);
+          y[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = y[i];
+        if (APPLY && live) {
+          double* o = out + (t * S + s) * N;
+#pragma unroll
+          for (int i = 0; i < N; ++i) __stcs(o + i, x[i]);
+        }
+      }
+    });
+    hi -= kTile;
   }
-  if (!APPLY) {
+  if (!APPLY && live) {
 #pragma unroll
     for (int i = 0; i < N; ++i) out[(c * S + s) * N + i] = x[i];
   }
@@ -141,13 +191,33 @@ __global__ void k_sample_mid(const double* __restrict__ G, const double* __restr
   double x[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) x[i] = 0.0;
+  // the recursion is a chain of P dependent mat-vecs; G_c and e_c do not depend on it, so the next chunk's are
+  // loaded while the current one is applied (otherwise every step pays an exposed L2 / DRAM round trip)
+  double Gn[N][N], en[N];
+  auto load = [&](long long c) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      en[i] = ebuf[(c * S + s) * N + i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) Gn[i][j] = __ldg(G + c * N * N + i * N + j);
+    }
+  };
+  if (P > 1) load(P - 1);
   for (long long c = P - 1; c >= 1; --c) {   // xb[0] is never read
+    double Gc[N][N], ec[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      ec[i] = en[i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) Gc[i][j] = Gn[i][j];
+    }
+    if (c > 1) load(c - 1);
     double y[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      double a = ebuf[(c * S + s) * N + i];
+      double a = ec[i];
 #pragma unroll
-      for (int j = 0; j < N; ++j) a = fma(__ldg(G + c * N * N + i * N + j), x[j], a);
+      for (int j = 0; j < N; ++j) a = fma(Gc[i][j], x[j], a);
       y[i] = a;
     }
 #pragma unroll
