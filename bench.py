@@ -296,8 +296,29 @@ def run_psqrt(args):
                 graph_note = f"eager launches ({e})"
                 one_pass = eager_pass
     else:
-        def one_pass():
+        def eager_pass():
             return _lib.filter_smoother(ssm, ys, m0, L0, smooth=True, loglik=False, chunk_len=args.chunk)
+
+        one_pass = eager_pass
+        graph_note = "eager launches"
+        if os.environ.get("PSQRT_GRAPH", "1") != "0":
+            # the five kernels of a pass replayed from one CUDA graph: no launch gaps, no per-step host work
+            try:
+                for _ in range(3):
+                    eager_pass()
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    graph_out = eager_pass()
+                torch.cuda.synchronize()
+
+                def one_pass():
+                    graph.replay()
+                    return graph_out
+                graph_note = "one CUDA graph per pass"
+            except Exception as e:       # capture not possible on this system: eager launches
+                graph_note = f"eager launches ({e})"
+                one_pass = eager_pass
 
     def barrier():
         if world > 1:
@@ -451,7 +472,7 @@ def run_psqrt(args):
                                       "`exchange`)" if world > 1 else ""),
                        "nx": NX, "ny": NY, "T_per_gpu": T, "T_total": T * world, "chunk_len": plan.chunk_len,
                        "parallelism": f"time-shard x{world}" if world > 1 else "single GPU",
-                       "launch": (graph_note if world > 1 else "eager launches"),
+                       "launch": graph_note,
                        "exchange": (None if world == 1 else
                                     ("P2P stores into peer-mapped buffers + flags (psqrt_peer_push / psqrt_peer_wait)"
                                      if sharded.exchange == "peer" else
