@@ -75,23 +75,24 @@ __global__ void k_sample_gprod(const double* __restrict__ E, long long n_el, int
 }
 
 // APPLY = false: e_c (from x = 0) -> ebuf[c][s];  APPLY = true: from the boundary state xb[c + 1][s], writing samples.
-// All 128 threads of a CTA work on the SAME chunk (consecutive samples), so the coefficients (g_t, E_t, sign-
-// normalised D_t) of a tile of kTile steps are staged once per CTA in shared memory -- fetched into registers while
+// All threads of a CTA work on the SAME chunk (consecutive samples), so the coefficients (g_t, E_t, sign-
+// normalised D_t) of a tile of TILE steps are staged once per CTA in shared memory -- fetched into registers while
 // the previous tile is being processed, so their latency is hidden -- and read back as broadcasts; each thread's
 // draws come through a 4-deep register ring (loads issued 4 steps ahead of their use).  ncu on the first version
 // (coefficients and draws loaded at the point of use): 18-24 warps per issue stalled on long_scoreboard.
-constexpr int kTile = 16;
-
-template <int N, bool APPLY>
-__global__ void __launch_bounds__(128, 4)
+// BS = threads per CTA, TILE = steps staged at a time: 128 / 16 normally, 32 / 4 when there are at most 32 samples
+// (a 128-thread CTA would be three quarters idle and cap the number of resident chunks).
+template <int N, bool APPLY, int BS, int TILE>
+__global__ void __launch_bounds__(BS, BS == 32 ? 16 : 4)
 k_sample_sweep(const double* __restrict__ g, const double* __restrict__ E, const double* __restrict__ D,
                const double* __restrict__ eps, long long n_el, long long S, int K, long long P,
                const double* __restrict__ xb, double* __restrict__ out) {
   constexpr int NN = N * N, NC = N + 2 * NN;          // per step: g [N], E [N][N], D [N][N]
-  constexpr int NV = (kTile * NC + 127) / 128;        // staged values per thread and tile
-  __shared__ double coef[kTile * NC];
+  static_assert(TILE % 4 == 0, "the draw ring has 4 slots");
+  constexpr int NV = (TILE * NC + BS - 1) / BS;       // staged values per thread and tile
+  __shared__ double coef[TILE * NC];
   const int tid = threadIdx.x;
-  const long long s = (long long)blockIdx.x * 128 + tid;
+  const long long s = (long long)blockIdx.x * BS + tid;
   const bool live = s < S;                            // no early return: every thread stages and synchronises
   const long long c = blockIdx.y;
   const long long k0 = c * K, k1 = (k0 + K < n_el) ? k0 + K : n_el;
@@ -103,11 +104,11 @@ k_sample_sweep(const double* __restrict__ g, const double* __restrict__ E, const
   auto fetch = [&](long long hi) {                     // coefficients of steps hi, hi - 1, ... -> registers
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int idx = tid + v * 128;
+      const int idx = tid + v * BS;
       const int u = idx / NC, f = idx % NC;
       const long long t = hi - u;
       double val = 0.0;
-      if (idx < kTile * NC && t >= k0) {
+      if (idx < TILE * NC && t >= k0) {
         if (f < N) {
           val = __ldg(g + t * N + f);
         } else if (f < N + NN) {
@@ -140,13 +141,13 @@ k_sample_sweep(const double* __restrict__ g, const double* __restrict__ E, const
     __syncthreads();                                   // the previous tile has been read by everyone
 #pragma unroll
     for (int v = 0; v < NV; ++v)
-      if (tid + v * 128 < kTile * NC) coef[tid + v * 128] = sv[v];
+      if (tid + v * BS < TILE * NC) coef[tid + v * BS] = sv[v];
     __syncthreads();
-    if (hi - kTile >= k0) fetch(hi - kTile);           // in flight during this tile's steps
+    if (hi - TILE >= k0) fetch(hi - TILE);             // in flight during this tile's steps
 #pragma unroll 1
-    for (int u0 = 0; u0 < kTile; u0 += 4)              // rolled: registers stay low enough for ~16 warps per SM
+    for (int u0 = 0; u0 < TILE; u0 += 4)               // rolled: registers stay low enough for ~16 warps per SM
     static_for_s<0, 4>([&](auto uc) {
-      constexpr int slot = decltype(uc)::value;        // ring slot = step index mod 4 (kTile is a multiple of 4)
+      constexpr int slot = decltype(uc)::value;        // ring slot = step index mod 4 (TILE is a multiple of 4)
       const int u = u0 + slot;
       const long long t = hi - u;
       if (t >= k0) {                                   // uniform over the CTA
@@ -174,7 +175,7 @@ k_sample_sweep(const double* __restrict__ g, const double* __restrict__ E, const
         }
       }
     });
-    hi -= kTile;
+    hi -= TILE;
   }
   if (!APPLY && live) {
 #pragma unroll
@@ -264,7 +265,8 @@ int run(const double* g, const double* E, const double* D, const double* eps, do
         long long S, void* ws, size_t ws_bytes, cudaStream_t st) {
   const SamplerPlan p = sampler_plan(N, n_el, S);
   if (p.P > 1 && (!ws || ws_bytes < p.bytes)) return PSQRT_EWORKSPACE;
-  const unsigned bs = 128;
+  const bool narrow = S <= 32;
+  const unsigned bs = narrow ? 32 : 128;
   const dim3 grid((unsigned)((S + bs - 1) / bs), (unsigned)p.P, 1);
   double* Gc = nullptr;
   double* eb = nullptr;
@@ -275,10 +277,12 @@ int run(const double* g, const double* E, const double* D, const double* eps, do
     eb = reinterpret_cast<double*>(w + p.e_off);
     xb = reinterpret_cast<double*>(w + p.x_off);
     k_sample_gprod<N><<<(unsigned)((p.P + 127) / 128), 128, 0, st>>>(E, n_el, p.K, p.P, Gc);
-    k_sample_sweep<N, false><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, nullptr, eb);
+    if (narrow) k_sample_sweep<N, false, 32, 4><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, nullptr, eb);
+    else k_sample_sweep<N, false, 128, 16><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, nullptr, eb);
     k_sample_mid<N><<<(unsigned)((S + 127) / 128), 128, 0, st>>>(Gc, eb, S, p.P, xb);
   }
-  k_sample_sweep<N, true><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, xb, samples);
+  if (narrow) k_sample_sweep<N, true, 32, 4><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, xb, samples);
+  else k_sample_sweep<N, true, 128, 16><<<grid, bs, 0, st>>>(g, E, D, eps, n_el, S, p.K, p.P, xb, samples);
   return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA;
 }
 
