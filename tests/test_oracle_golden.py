@@ -289,3 +289,33 @@ def test_get_conditional_model_vs_reference_source():
         np.testing.assert_allclose(LLt(ch), LLt(b @ q.chol), atol=1e-10)
     with pytest.raises(NotImplementedError):
         O.get_conditional_model(lambda x, q: a @ x + np.ones((2, 3)) @ q, O.MVNSqrt(np.zeros(3), np.eye(3)), O.extended)
+
+
+def test_loglikelihood_tangent_vs_finite_differences():
+    """Groundwork for the gradient row: the oracle's forward-mode tangent of the log-likelihood
+    equals central finite differences of the (reference-pinned) parallel filter's ell, for a parameter in the
+    observation noise factor (the `r` of the bearings experiment) and one in the transition matrix."""
+    case = lgssm_case(3, 2, 60, seed=5)
+    T = case["ys"].shape[0]
+    tile = lambda a: np.broadcast_to(a, (T,) + a.shape).copy()
+    dirs = {
+        "cholR": np.array([[1.0, 0.0], [0.3, 0.5]]),
+        "F": np.array([[0.2, -0.1, 0.0], [0.0, 0.1, 0.3], [0.05, 0.0, -0.2]]),
+    }
+
+    def ell_at(name, eps):
+        c2 = dict(case)
+        c2[name] = case[name] + eps * dirs[name]
+        tm, om = oracle_lgssm_models(c2)
+        _, ell = O.par_filtering(c2["ys"], O.MVNSqrt(c2["m0"], c2["L0"]), tm, om, O.extended, None, True)
+        return ell
+
+    names = ("F", "cholQ", "b", "H", "cholR", "c")
+    ssm = tuple(tile(case[k]) for k in names)
+    for name, direction in dirs.items():
+        dssm = tuple(tile(direction) if k == name else np.zeros_like(s_) for k, s_ in zip(names, ssm))
+        ell, dell = O.seq_loglikelihood_jvp(ssm, dssm, case["m0"], case["L0"], case["ys"])
+        assert abs(ell - ell_at(name, 0.0)) <= 1e-10 * abs(ell)
+        h = 1e-5
+        fd = (ell_at(name, h) - ell_at(name, -h)) / (2 * h)
+        assert abs(dell - fd) <= 1e-6 * max(1.0, abs(fd)), (name, dell, fd)
