@@ -195,34 +195,110 @@ def cpu_pass_rate(model, T_sample, threads, seed=123):
     return T_sample / dt, dt
 
 
+def cpu_sequential_rate(model, T_sample, seed=123):
+    """steps/s of the NumPy restatement of the reference's SEQUENTIAL sqrt filter + smoother (one core: a step
+    loop of _sqrt_predict / _sqrt_update / _sqrt_smooth, sequential/_filtering.py:80-108, _smoothing.py:60-77)."""
+    import parsmooth_np as O
+    ys = simulate(model, T_sample, seed)
+    tm = O.FunctionalModel(O.lgssm_function(model["F"]), O.MVNSqrt(model["b"], model["cholQ"]))
+    om = O.FunctionalModel(O.lgssm_function(model["H"]), O.MVNSqrt(model["c"], model["cholR"]))
+    x0 = O.MVNSqrt(model["m0"], model["L0"])
+    t0 = time.perf_counter()
+    O.filter_smoother(ys, x0, tm, om, O.extended, None, False)
+    dt = time.perf_counter() - t0
+    return T_sample / dt, dt
+
+
+def _jax_reference():
+    """The UNMODIFIED reference (parsmooth on JAX) if this image can import it: BASELINE.md section 3.  Returns a
+    function T -> (seconds per jitted filter_smoother call, parallel=True) or None with the reason."""
+    try:
+        import jax  # noqa: F401
+    except Exception as e:      # not installed in this image, no wheel in /opt/wheelhouse, no network
+        return None, f"import jax failed: {type(e).__name__}: {e}"
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "parsmooth")) and cand not in sys.path:
+            sys.path.insert(0, cand)
+    try:
+        import jax
+        import jax.numpy as jnp
+        jax.config.update("jax_enable_x64", True)
+        jax.config.update("jax_platform_name", "cpu")
+        from functools import partial
+        from parsmooth import FunctionalModel as FM, MVNSqrt as MS
+        from parsmooth.linearization import extended as jext
+        from parsmooth.methods import filter_smoother as jfs
+    except Exception as e:
+        return None, f"import parsmooth failed: {type(e).__name__}: {e}"
+
+    def run(model, ys, parallel):
+        f = lambda x, A: jnp.dot(A, x)
+        tm = FM(partial(f, A=jnp.asarray(model["F"])), MS(jnp.asarray(model["b"]), jnp.asarray(model["cholQ"])))
+        om = FM(partial(f, A=jnp.asarray(model["H"])), MS(jnp.asarray(model["c"]), jnp.asarray(model["cholR"])))
+        x0 = MS(jnp.asarray(model["m0"]), jnp.asarray(model["L0"]))
+        fn = jax.jit(lambda y: jfs(y, x0, tm, om, jext, None, parallel))
+        y = jnp.asarray(ys)
+        jax.block_until_ready(fn(y))          # compile + warm-up, as the reference's notebooks do
+        t0 = time.perf_counter()
+        jax.block_until_ready(fn(y))
+        return time.perf_counter() - t0
+    return run, None
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores, same workload definition
+    (C1 LGSSM nx=4 ny=2, one parallel sqrt filter_smoother pass over T=1e6 steps per step).  JAX when importable
+    (BASELINE.md section 3); otherwise the NumPy restatement (oracle port), said so in the line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
     model = make_lgssm(NX, NY)
-    T_sample = 100_000
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_pass_rate(model, 10_000, threads)
-    rates, times = [], []
-    for _ in range(args.steps):
-        r, dt = cpu_pass_rate(model, T_sample, threads)
-        rates.append(r)
+    T = args.T
+    budget_s = float(os.environ.get("PSQRT_REF_BUDGET_S", "150"))
+    jax_run, why = _jax_reference()
+    times = []
+    seq = None
+    if jax_run is not None:
+        kind, ys = "reference", simulate(model, T, 123)
+        dt = jax_run(model, ys, True)
         times.append(dt)
-    value = T_sample * len(times) / sum(times)
-    sample = (f"NumPy restatement of parsmooth's parallel sqrt filter+smoother (associative_scan, batched LAPACK QR "
-              f"split over {threads} threads), T={T_sample} sample of the T=1e6 workload, per-step rate")
+        while len(times) < args.steps and sum(times) + dt < budget_s:
+            times.append(jax_run(model, ys, True))
+        Ts = min(T, 20_000)
+        seq = {"value": Ts / jax_run(model, ys[:Ts], False), "unit": "steps/s", "cores": 1,
+               "sample": f"jax.jit(filter_smoother, parallel=False), T={Ts} prefix"}
+        sample = f"jax.jit(parsmooth.filter_smoother, parallel=True) on CPU, fp64, T={T} (the full workload)"
+    else:
+        kind = "port"
+        cpu_pass_rate(model, 10_000, threads)                 # warm-up (thread pool, LAPACK)
+        _, dt = cpu_pass_rate(model, T, threads)
+        times.append(dt)
+        while len(times) < args.steps and sum(times) + dt < budget_s:
+            times.append(cpu_pass_rate(model, T, threads)[1])
+        Ts = 20_000
+        r_seq, dt_seq = cpu_sequential_rate(model, Ts)
+        seq = {"value": r_seq, "unit": "steps/s", "cores": 1,
+               "sample": f"NumPy restatement of the SEQUENTIAL sqrt filter+smoother, T={Ts} sample ({dt_seq:.1f} s)"}
+        sample = (f"NumPy restatement of parsmooth's parallel sqrt filter+smoother (associative_scan, batched LAPACK QR "
+                  f"split over {threads} threads), T={T} (the full workload), {len(times)} timed pass(es) of "
+                  f"{args.steps} requested (bounded to ~{budget_s:.0f} s)")
+    value = T * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C1 LGSSM nx=4 ny=2, one filter_smoother pass; CPU arm times a T=1e5 sample",
-                   "nx": NX, "ny": NY, "T_sample": T_sample},
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": f"C1 LGSSM nx={NX} ny={NY}, T={T:.0e}, one parallel sqrt filter_smoother pass per step "
+                               "(CPU arm: the same workload on the host cores)",
+                   "nx": NX, "ny": NY, "T_per_gpu": T, "same_config": True},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample,
+                         "sequential": seq},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "JAX/jaxlib are not installed and not in /opt/wheelhouse: the unmodified reference cannot run; "
-                "this arm is the oracle port (see DESIGN.md).",
     }
+    if jax_run is None:
+        line["note"] = (f"unmodified reference not runnable here ({why}; no jax wheel in /opt/wheelhouse, no "
+                        "network): this arm is the oracle port (see DESIGN.md)")
     print(json.dumps(line))
     return 0
 
@@ -230,6 +306,158 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # psqrt arm
 # --------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the NUMA node the GPU's
+    PCIe root hangs off, so that N ranks do not all stage their copies through node 0."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        return None
+    return None
+
+
+def sharded_parity(world, rank, dev, exchange):
+    """Correctness of the time-sharded pass, checked in the same run that times it (N > 1): one sequence of
+    world x 5e4 steps smoothed (a) time-sharded over the ranks, three passes in a row (slot reuse / epochs of the peer
+    exchange), smoother + log-likelihood and a filter-only pass, and (b) unsharded on every rank's own GPU;
+    rank 0 also checks the filtered prefix against the oracle (CPU restatement of the reference, used as the
+    checker only).  Returns the dict printed under "parity"."""
+    import torch
+    import torch.distributed as dist
+    from psqrt import _lib, dist as pdist
+    from psqrt._lib import LinearizedSSM
+    Tl = 50_000
+    model = make_lgssm(NX, NY)
+    ys_full = simulate(model, Tl * world, seed=7)
+    g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    names = ("F", "cholQ", "b", "H", "cholR", "c")
+    ssm = LinearizedSSM(*[g(model[k]) for k in names], host={k: model[k] for k in names})
+    m0, L0 = g(model["m0"]), g(model["L0"])
+    fm_ref, fL_ref, sm_ref, sL_ref, ell_ref = _lib.filter_smoother(ssm, g(ys_full), m0, L0, smooth=True, loglik=True)
+    y_loc = g(ys_full[rank * Tl:(rank + 1) * Tl])[None].contiguous()
+    sh = pdist.TimeShardedSmoother(NX, NY, Tl, device=dev, exchange=exchange)
+    for _ in range(3):
+        fm, fL, sm, sL, ell = sh.filter_smoother(ssm, y_loc, m0[None], L0[None], smooth=True, loglik=True)
+    for _ in range(2):
+        ffm, ffL, _, _, _ = sh.filter_smoother(ssm, y_loc, m0[None], L0[None], smooth=False, loglik=False)
+    torch.cuda.synchronize()
+    sl = slice(rank * Tl, (rank + 1) * Tl + 1)
+    LLt = lambda L: L @ L.transpose(-1, -2)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    errs = [rel(sm[0], sm_ref[sl]), rel(LLt(sL[0]), LLt(sL_ref[sl])), float((ell[0] - ell_ref).abs() / ell_ref.abs()),
+            max(rel(ffm[0][1:], fm_ref[sl][1:]), rel(fm[0][1:], fm_ref[sl][1:])),
+            max(rel(LLt(ffL[0][1:]), LLt(fL_ref[sl][1:])), rel(LLt(fL[0][1:]), LLt(fL_ref[sl][1:])))]
+    t = torch.tensor(errs, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"T_local": Tl, "vs": "unsharded pass on one GPU (every rank) + oracle filtered prefix (rank 0)",
+           "max_rel_mean": float(t[0]), "max_rel_LLt": float(t[1]), "rel_ell": float(t[2]),
+           "max_rel_filtered_mean": float(t[3]), "max_rel_filtered_LLt": float(t[4]), "exchange": sh.exchange}
+    ok = bool(t[0] < 1e-9 and t[1] < 1e-9 and t[2] < 1e-8 and t[3] < 1e-9 and t[4] < 1e-9)
+    if rank == 0:
+        import parsmooth_np as O
+        n_or = 4000
+        tm = O.FunctionalModel(O.lgssm_function(model["F"]), O.MVNSqrt(model["b"], model["cholQ"]))
+        om = O.FunctionalModel(O.lgssm_function(model["H"]), O.MVNSqrt(model["c"], model["cholR"]))
+        of = O.filtering(ys_full[:n_or], O.MVNSqrt(model["m0"], model["L0"]), tm, om, O.extended, None, True)
+        gm, gL = fm[0][1:n_or + 1].cpu().numpy(), fL[0][1:n_or + 1].cpu().numpy()
+        om_, oL_ = np.asarray(of.mean)[1:], np.asarray(of.chol)[1:]
+        e1 = float(np.abs(gm - om_).max() / np.abs(om_).max())
+        oP = oL_ @ np.swapaxes(oL_, -1, -2)
+        e2 = float(np.abs(gL @ np.swapaxes(gL, -1, -2) - oP).max() / np.abs(oP).max())
+        out["oracle_prefix"] = {"steps": n_or, "max_rel_mean": e1, "max_rel_LLt": e2}
+        ok = ok and e1 < 1e-9 and e2 < 1e-9
+    flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item() > 0.5)
+    return out
+
+
+def c4_strong(world, rank, dev, steps=5):
+    """BASELINE.json configs[3]: LGSSM nx=8 ny=4, T = 1e7 steps IN TOTAL, time-sharded over the ranks (strong
+    scaling); one filter_smoother pass per step, replayed from a CUDA graph.  Observations are iid N(0,1) generated on
+    the device (no kernel branches on data: timing is data-independent)."""
+    import torch
+    import torch.distributed as dist
+    from psqrt import _lib, dist as pdist
+    from psqrt._lib import LinearizedSSM
+    nx, ny, T_total = 8, 4, 10_000_000
+    if not _lib.supported(nx, ny):
+        return {"unavailable": "nx=8 not compiled in"}
+    Tl = T_total // world
+    model = make_lgssm(nx, ny, seed=1)
+    g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    names = ("F", "cholQ", "b", "H", "cholR", "c")
+    ssm = LinearizedSSM(*[g(model[k]) for k in names], host={k: model[k] for k in names})
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    y = torch.randn((1, Tl, ny), dtype=torch.float64, device=dev, generator=gen)
+    m0, L0 = g(model["m0"])[None].contiguous(), g(model["L0"])[None].contiguous()
+    if world > 1:
+        sh = pdist.TimeShardedSmoother(nx, ny, Tl, device=dev, exchange=os.environ.get("PSQRT_EXCHANGE", "peer"))
+        eager = lambda: sh.filter_smoother(ssm, y, m0, L0)
+    else:
+        eager = lambda: _lib.filter_smoother(ssm, y, m0, L0, smooth=True, loglik=False)
+    one, launch = eager, "eager launches"
+    try:
+        for _ in range(2):
+            eager()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            if sh.exchange != "peer":
+                raise RuntimeError("exchange is NCCL")
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            eager()
+        torch.cuda.synchronize()
+        one, launch = graph.replay, "one CUDA graph per pass"
+    except Exception as e:
+        launch = f"eager launches ({e})"
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= steps
+    hbm = algorithmic_bytes_per_step(nx)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    value = T_total / (ms * 1e-3)
+    del y
+    torch.cuda.empty_cache()
+    return {"workload": f"LGSSM nx={nx} ny={ny}, T_total={T_total:.0e} time-sharded over {world} GPU(s) "
+                        f"({Tl} steps each), one filter_smoother pass", "scaling": "strong", "ms_per_step": ms,
+            "value": value, "unit": "steps/s", "steps": steps, "launch": launch,
+            "frac_of_hbm_bound_per_gpu": value / world / (peak * 1e9 / hbm),
+            "note": "strong-scaling efficiency = value(N) / (N x value(1)); computed by the reader from the N=1 line"}
+
+
 def run_psqrt(args):
     import torch
     import torch.distributed as dist
@@ -245,9 +473,22 @@ def run_psqrt(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the psqrt arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+
+    # ---- N > 1: the sharded pass is CHECKED before it is timed ---------------------------------------
+    parity = None
+    if world > 1:
+        parity = sharded_parity(world, rank, dev, os.environ.get("PSQRT_EXCHANGE", "peer"))
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "error": "sharded pass failed its parity check",
+                                  "parity": parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            return 1
 
     T = args.T
     model = make_lgssm(NX, NY)
@@ -353,18 +594,17 @@ def run_psqrt(args):
     out_L = torch.empty((T + 1, NX, NX), dtype=torch.float64).pin_memory()
 
     def e2e_pass():
-        y_dev = ys_host.to(dev, non_blocking=True)
         if world > 1:
-            fm, fL, sm, sL, _ = one_pass_from(y_dev)
+            # the sharded pass replays from its CUDA graph on the static input buffer: H2D into that buffer, replay,
+            # D2H of the smoothed shard
+            ys.copy_(ys_host, non_blocking=True)
+            fm, fL, sm, sL, _ = one_pass()
         else:
+            y_dev = ys_host.to(dev, non_blocking=True)
             res = psqrt.filter_smoother(y_dev, x0, tm, om, psqrt.linearization.extended, None, True)
             sm, sL = res.mean, res.chol
         out_m.copy_(sm.reshape(out_m.shape), non_blocking=True)
         out_L.copy_(sL.reshape(out_L.shape), non_blocking=True)
-
-    if world > 1:
-        def one_pass_from(y_dev):
-            return sharded.filter_smoother(ssm, y_dev[None], m0[None], L0[None])
 
     for _ in range(2):
         e2e_pass()
@@ -423,10 +663,12 @@ def run_psqrt(args):
         achieved = share[dom] * T / (stages[dom] * 1e-3) / 1e9
         # whole pass, per GPU: B(n) bytes per step over the time of the complete pass
         pass_achieved = algorithmic_bytes_per_step(NX) * (T / (ms_per_step * 1e-3)) / 1e9
+        # DRAM bytes of the dominant stage per launch, from the committed `ncu --set full` capture of this exact
+        # configuration (profiles/r02_dram_traffic.json, keyed by nx/ny/T); null for any other configuration
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")      # from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
+            traffic = json.load(open(tpath)).get(f"nx{NX}_ny{NY}_T{T}", {}).get(dom)
         fp64_peak = measure_fp64_peak(dev)
         fp64_src = "measured live (psqrt_fp64_probe: independent DFMA chains, 16 warps/SM)"
         if fp64_peak is None:
@@ -460,6 +702,15 @@ def run_psqrt(args):
                         "sample": f"NumPy restatement of the reference's parallel sqrt filter+smoother on a T=1e5 "
                                   f"sample of the same LGSSM ({dt:.1f} s), LAPACK QR batch split over {threads} threads"}
 
+    # ---- secondary: BASELINE.json configs[3], strong scaling (nx=8, ny=4, T_total=1e7) ------------
+    secondary = {}
+    if (NX, NY) == (4, 2) and T == T_PER_GPU and not args.no_secondary:
+        try:
+            res = c4_strong(world, rank, dev)
+        except Exception as e:      # informational line: never fails the metric
+            res = {"unavailable": repr(e)}
+        secondary["c4_strong"] = res
+
     if rank == 0:
         plan = _lib.get_plan(NX, NY, T, 1, 0)
         line = {
@@ -485,6 +736,12 @@ def run_psqrt(args):
             "e2e": e2e, "gpu_launches": (5 if world == 1 else (11 if sharded.exchange == "peer" else 7)) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if numa is not None:
+            line["config"]["host_numa_node_rank0"] = numa
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -493,18 +750,29 @@ def run_psqrt(args):
 
 
 def run_bearings(args):
-    """Secondary workload (BASELINE.json configs[1]): bearings-only coordinated-turn tracking, nx = 5, 2 sensors,
+    """Secondary workloads.  BASELINE.json configs[1]: bearings-only coordinated-turn tracking, nx = 5, 2 sensors,
     T = 1e5, iterated sqrt extended (or cubature / Gauss-Hermite) parallel smoother, 10 iterations, through the public
-    API (psqrt.methods.iterated_smoothing).  Prints one informational JSON line; not the driver's metric."""
+    API (psqrt.methods.iterated_smoothing).  configs[4] (--runs 100 --T 10000 --iters 20 --batched): independent
+    Monte-Carlo runs, dealt round-robin over the ranks under torchrun (psqrt.dist.iterated_smoothing_batch_sharded:
+    no data-path collective, the log-likelihoods gathered at the end).  One informational JSON line; not the driver's
+    metric."""
     import torch
+    import torch.distributed as dist
     import psqrt
     from psqrt.models import bearings
-    dev = torch.device("cuda", 0)
+    from psqrt import dist as pdist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     T = args.T if args.T != T_PER_GPU else 100_000
     s1, s2, r, dt, qc, qw = np.array([-1.5, 0.5]), np.array([1.0, 1.0]), 0.5, 0.01, 0.01, 0.1
-    runs = max(args.runs, 1)      # > 1: BASELINE.json configs[4], independent Monte-Carlo runs one after the other
-    ys_all = [bearings.get_data(np.array([0.1, 0.2, 1.0, 0.0]), dt, r, T, s1, s2, random_state=k)[2] for k in range(runs)]
-    ys = ys_all[0]
+    runs = max(args.runs, 1)      # > 1: BASELINE.json configs[4], independent Monte-Carlo runs
+    mine = pdist.batch_indices(runs, world, rank)
+    ys_all = {k: bearings.get_data(np.array([0.1, 0.2, 1.0, 0.0]), dt, r, T, s1, s2, random_state=k)[2] for k in mine}
     Q, R, obs_f, trans_f = bearings.make_parameters(qc, qw, r, dt, s1, s2)
     g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
     x0 = psqrt.MVNSqrt(np.array([-4.0, -1.0, 2.0, 7.0, 3.0]), np.eye(5))
@@ -512,16 +780,27 @@ def run_bearings(args):
     om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(np.zeros(2), np.linalg.cholesky(R)))
     nominal = psqrt.MVNSqrt(g(np.tile(np.array([-1.0, -1.0, 6.0, 4.0, 2.0]), (T + 1, 1))),
                             torch.eye(5, dtype=torch.float64, device=dev).expand(T + 1, 5, 5))
-    ys_ds = [g(y.astype(np.float64)) for y in ys_all]
+    ys_ds = [g(ys_all[k].astype(np.float64)) for k in mine]
     lin = getattr(psqrt.linearization, args.lin)
     n_iter = args.iters
+    ys_batch = torch.stack(ys_ds) if (args.batched and ys_ds) else None
 
-    ys_batch = torch.stack(ys_ds) if args.batched else None
+    class _Runs:          # per-run observations, indexable by run number (only this rank's runs are resident)
+        def __len__(self):
+            return runs
+
+        def __getitem__(self, i):
+            return ys_ds[mine.index(i)]
 
     def run():
-        if args.batched:     # all runs in ONE pass per iteration (batch axis of the kernels)
-            from psqrt.dist import iterated_smoothing_batched
-            return iterated_smoothing_batched(ys_batch, x0, tm, om, lin, nominal, n_iter=n_iter)
+        if args.batched and runs > 1:
+            # config 5 through its driver: runs dealt round-robin, this rank's share smoothed as ONE batch per
+            # iteration, log-likelihoods (robustness_100runs.py:60-66) gathered at the end
+            _, nom, _ = pdist.iterated_smoothing_batch_sharded(_Runs(), x0, tm, om, lin, nominal, n_iter=n_iter,
+                                                               return_loglikelihood=True)
+            return nom
+        if args.batched:
+            return pdist.iterated_smoothing_batched(ys_batch, x0, tm, om, lin, nominal, n_iter=n_iter)
         res = None
         for ys_d in ys_ds:
             res = psqrt.iterated_smoothing(ys_d, x0, tm, om, lin, nominal, True, criterion=lambda i, *_: i < n_iter)
@@ -530,6 +809,8 @@ def run_bearings(args):
     for _ in range(max(args.warmup, 2)):
         run()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -537,13 +818,23 @@ def run_bearings(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"workload": f"bearings-only CT nx=5 ny=2 T={T}, iterated sqrt {args.lin} parallel smoother, "
-                                  f"{n_iter} iterations" + (f", {runs} independent runs "
-                                                            + ("as one batch" if args.batched else "in sequence")
-                                                            + " (BASELINE.json configs[4])" if runs > 1
-                                                            else " (BASELINE.json configs[1])"),
-                      "ms_per_call": ms, "value": runs * T * n_iter / (ms * 1e-3), "unit": "step-passes/s",
-                      "finite": bool(torch.isfinite(res.mean).all().item())}))
+    finite = True if res is None else bool(torch.isfinite(res.mean).all().item())
+    if world > 1:
+        t = torch.tensor([ms, 0.0 if finite else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, finite = float(t[0]), bool(t[1] == 0)
+    if rank == 0:
+        print(json.dumps({"workload": f"bearings-only CT nx=5 ny=2 T={T}, iterated sqrt {args.lin} parallel smoother, "
+                                      f"{n_iter} iterations" + (f", {runs} independent runs "
+                                                                + ("as one batch per GPU" if args.batched else "in sequence")
+                                                                + " (BASELINE.json configs[4])" if runs > 1
+                                                                else " (BASELINE.json configs[1])"),
+                          "n_gpus": world, "parallelism": f"batch-shard x{world} (round-robin, no collective)" if world > 1 else "single GPU",
+                          "ms_per_call": ms, "value": runs * T * n_iter / (ms * 1e-3), "unit": "step-passes/s",
+                          "finite": finite}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -555,6 +846,7 @@ def main():
     ap.add_argument("--impl", default="psqrt", choices=["psqrt", "reference"])
     ap.add_argument("--T", type=int, default=T_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the informational nx=8 T=1e7 strong-scaling line")
     ap.add_argument("--no-host-model", action="store_true", help="load the model from HBM per step instead of by value")
     ap.add_argument("--chunk", type=int, default=0, help="chunk length override (0 = library default)")
     ap.add_argument("--workload", default="lgssm", choices=["lgssm", "bearings"],

@@ -98,22 +98,51 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
 
 /* ---- staged calls for a time-sharded run (one shard per GPU) --------
  * 1. psqrt_filter_reduce  : local chunk summaries + shard total  -> ftotal [B, nf_filter]
- * 2. (all-gather ftotal over ranks)  psqrt_carry_filter: fold totals of ranks < rank into x0
+ * 2. (exchange of the R totals)  psqrt_carry_filter: the totals of ranks < rank folded into x0
  * 3. psqrt_filter_apply   : filtered trajectory of the shard from the carry-in state, ell
  *                           partial; with stotal != NULL also the smoothing reduce -> stotal
- * 4. (all-gather stotal + last rank's terminal state)  psqrt_carry_smoother
- * 5. psqrt_smoother_apply : smoothed trajectory of the shard from the carry-in state.
- * The same workspace must be passed to 1, 3 and 5. */
+ * 4. (exchange of the R smoothing totals + the last rank's terminal state)  psqrt_carry_smoother
+ * 5. psqrt_smoother_apply : smoothed trajectory of the shard from the carry-in state; fm / fL must be the arrays
+ *                           the psqrt_filter_apply of the same pass wrote (its workspace holds their packed copy).
+ * The same workspace must be passed to 1, 3 and 5.  The carries are log-depth scans of the R totals.
+ *
+ * The exchange itself (steps 2 and 4) is either the caller's (peer = NULL: e.g. two NCCL all-gathers; totals
+ * [R, B, nf] are then passed to the carry calls) or FUSED into these kernels over peer-mapped memory
+ * (peer != NULL; NVLink / NVSwitch P2P, e.g. CUDA IPC or torch symmetric memory):
+ *   - every rank owns ONE exchange buffer of psqrt_peer_layout(...) 8-byte words, zeroed once, mapped into all
+ *     ranks; `bufs` is a DEVICE array of the n_ranks base pointers as seen from this rank;
+ *   - the CTA that finishes the mid-level scan of psqrt_filter_reduce (psqrt_filter_apply) stores the shard total
+ *     (and, for the smoother phase, the shard's last filtered state) straight into slot `rank` of EVERY rank's
+ *     buffer, then publishes the pass number there;
+ *   - psqrt_carry_filter (psqrt_carry_smoother) waits, on the GPU and in stream order, until ALL ranks have
+ *     published that pass number and folds the totals it needs out of its local buffer (totals / mT / LT ignored).
+ * Pass numbers are counted on the device (one counter per sequence and phase) and the slots are double-buffered by
+ * pass parity: no per-pass host argument (a whole time-sharded pass replays from one CUDA graph), nothing is ever
+ * reset, and -- because every carry waits for all ranks -- no rank can run more than one pass ahead of a reader of
+ * its slot, also in filter-only passes. */
+typedef struct psqrt_peer {
+  void* const* bufs;        /* DEVICE array [n_ranks]: every rank's exchange buffer, mapped into this rank            */
+  int32_t rank, n_ranks;
+  int64_t batch;
+  int64_t flags_off, ctr_off, data_off, slot, payload;   /* 8-byte words; filled by psqrt_peer_layout               */
+} psqrt_peer;
+/* Fills the offsets of the two phases for (nx, n_ranks, batch) (bufs / rank are left to the caller) and returns the
+ * size of one rank's exchange buffer in 8-byte words (0: unsupported nx). */
+int64_t psqrt_peer_layout(int nx, int n_ranks, int64_t batch, psqrt_peer* filter_phase, psqrt_peer* smoother_phase);
+
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
-                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, void* stream);
+                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, const psqrt_peer* peer,
+                        void* stream);
 int psqrt_carry_filter(const double* totals /*[R,B,nf_filter]*/, int rank, int64_t batch, int nx,
-                       const double* m0, const double* L0, double* carry_m, double* carry_L, void* stream);
+                       const double* m0, const double* L0, double* carry_m, double* carry_L,
+                       const psqrt_peer* peer, void* stream);
 int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carry_m, const double* carry_L,
                        int nx, int ny, int64_t T, int64_t batch, int chunk_len, double* fm, double* fL,
-                       double* ell, double* stotal, void* ws, size_t ws_bytes, void* stream);
+                       double* ell, double* stotal, void* ws, size_t ws_bytes, const psqrt_peer* peer,
+                       void* stream);
 int psqrt_carry_smoother(const double* totals /*[R,B,nf_smoother]*/, int rank, int n_ranks, int64_t batch,
                          int nx, const double* mT, const double* LT, double* carry_m, double* carry_L,
-                         void* stream);
+                         const psqrt_peer* peer, void* stream);
 int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch,
                          int chunk_len, double* sm, double* sL, void* ws, size_t ws_bytes, void* stream);
@@ -191,27 +220,6 @@ int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id
                             const double* wm, const double* wc, int n_points, const double* nom_m,
                             const double* nom_L, int64_t count, const double* m_q, const double* chol_q,
                             double* F, double* chol, double* b, void* stream);
-
-/* ---- time-shard exchange over peer-mapped memory (NVLink / NVSwitch P2P) --------------------------------
- * The shard totals a time-sharded pass exchanges are a few hundred bytes: an NCCL all-gather
- * costs its launch + protocol latency (~20 us) twice per pass.  With every rank's exchange buffer mapped into
- * every peer (CUDA IPC / symmetric memory), psqrt_peer_push stores this rank's contribution straight into slot
- * `rank` of EVERY peer's buffer and then raises that peer's flag word; psqrt_peer_wait spins (on the GPU, in
- * stream order) until the flags of ranks [first, last] have reached `epoch`.  The carry kernels
- * (psqrt_carry_filter / psqrt_carry_smoother) then read the totals from the local buffer.
- *   peer_bufs  DEVICE array of n_ranks pointers: base of each peer's exchange buffer (doubles)
- *   peer_flags DEVICE array of n_ranks pointers: base of each peer's flag array (n_ranks 64-bit words, zeroed once)
- *   up to three segments (src[i], count[i] doubles) go to peer offsets dst_off[i] (doubles; slot of THIS rank)
- * Flags are monotonic epochs, so nothing is ever reset.  The epoch lives on the device (`epoch_ctr`, one 64-bit
- * word per exchange, zeroed once): a push publishes *epoch_ctr + 1, the wait that follows it in stream order
- * waits for that value and then stores it back -- no per-pass host argument, so a whole time-sharded pass
- * can be captured in a CUDA graph and replayed. */
-int psqrt_peer_push(const double* src0, int64_t count0, int64_t dst_off0, const double* src1, int64_t count1,
-                    int64_t dst_off1, const double* src2, int64_t count2, int64_t dst_off2,
-                    double* const* peer_bufs, unsigned long long* const* peer_flags, int rank, int n_ranks,
-                    const unsigned long long* epoch_ctr, void* stream);
-int psqrt_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr,
-                    void* stream);
 
 /* ---- measurement aid (bench.py): FP64 FMA throughput probe ------------------------------------
  * Launches 148 x 4 CTAs of 128 threads, each thread running 8 independent chains of `iters` x 16 dependent

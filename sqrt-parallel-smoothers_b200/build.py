@@ -28,7 +28,7 @@ ALL_NX = (1, 2, 3, 4, 5, 6, 8)    # state dimensions the dispatcher knows (psqrt
 # compiled state dimensions; PSQRT_NX_LIST="4,5" builds a development subset (the others then
 # report PSQRT_EUNSUPPORTED at run time)
 NX_LIST = tuple(int(v) for v in os.environ.get("PSQRT_NX_LIST", "").split(",") if v) or ALL_NX
-MAX_NY = 4                        # observation dimensions 1..MAX_NY for each of them
+MAX_NY = int(os.environ.get("PSQRT_MAX_NY", "4"))   # observation dimensions 1..MAX_NY for each nx (dev builds: fewer)
 _INC = re.compile(r'\s*#\s*include\s*"([^"]+)"')
 
 EXTRA = [f for f in os.environ.get("PSQRT_NVCC_EXTRA", "").split() if f]

@@ -4,6 +4,7 @@
 #include "../../include/psqrt.h"
 
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "psqrt_kernels.cuh"
 #include "psqrt_launch.h"
@@ -25,39 +26,6 @@ __global__ void __launch_bounds__(128) k_fp64_probe(double* out, int iters, doub
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += x[i];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// Time-shard exchange over peer-mapped memory (psqrt_peer_push / psqrt_peer_wait).  One CTA per peer.
-struct PushSeg {
-  const double* src;
-  long long count, dst_off;
-};
-__global__ void __launch_bounds__(128) k_peer_push(PushSeg s0, PushSeg s1, PushSeg s2, double* const* __restrict__ peer_bufs,
-                                                   unsigned long long* const* __restrict__ peer_flags, int rank,
-                                                   const unsigned long long* __restrict__ epoch_ctr) {
-  const unsigned long long epoch = *epoch_ctr + 1;   // bumped by the k_peer_wait that follows in stream order
-  double* dst = peer_bufs[blockIdx.x];
-  const PushSeg segs[3] = {s0, s1, s2};
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    for (long long k = threadIdx.x; k < segs[i].count; k += blockDim.x) dst[segs[i].dst_off + k] = segs[i].src[k];
-  __threadfence_system();   // this thread's stores are visible system-wide ...
-  __syncthreads();          // ... and so are every thread's, before the flag is raised
-  if (threadIdx.x == 0) {
-    volatile unsigned long long* f = peer_flags[blockIdx.x] + rank;
-    *f = epoch;
-  }
-}
-__global__ void k_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr) {
-  const unsigned long long epoch = *epoch_ctr + 1;
-  const int r = first + (int)threadIdx.x;
-  if (r <= last) {
-    const volatile unsigned long long* f = flags + r;
-    while (*f < epoch) __nanosleep(32);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) *epoch_ctr = epoch;
 }
 
 void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
@@ -175,6 +143,18 @@ const HostModel* host_model(const psqrt_ssm* s, bool need_obs, HostModel* out) {
 
 int check_launch() { return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA; }
 
+bool peer_ok(const psqrt_peer* p, int64_t batch) {
+  return p->bufs && p->n_ranks > 0 && p->rank >= 0 && p->rank < p->n_ranks && p->batch == batch && p->slot > 0 &&
+         p->payload > 0;
+}
+psq::PeerCtx peer_ctx(const psqrt_peer* p) {
+  psq::PeerCtx c;
+  c.bufs = reinterpret_cast<double* const*>(p->bufs);
+  c.rank = p->rank; c.n_ranks = p->n_ranks; c.batch = p->batch;
+  c.flags_off = p->flags_off; c.ctr_off = p->ctr_off; c.data_off = p->data_off; c.slot = p->slot; c.payload = p->payload;
+  return c;
+}
+
 bool ssm_ok(const psqrt_ssm* s, bool need_obs) {
   if (!s || !s->F || !s->cholQ || !s->b) return false;
   if (need_obs && (!s->H || !s->cholR || !s->c)) return false;
@@ -246,37 +226,52 @@ size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, i
 }
 
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
-                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, void* stream) {
+                        int chunk_len, double* ftotal, void* ws, size_t ws_bytes, const psqrt_peer* peer,
+                        void* stream) {
   if (!ssm_ok(ssm, true) || !y || ny <= 0) return PSQRT_EINVAL;
+  if (peer && !peer_ok(peer, batch)) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
+  if (peer && peer->payload != c.ln->nf_filter) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
   HostModel hmv;
   c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_own,
                        c.ws.chunk_pref, c.ws.warp_tot, c.ws.counter_f, st);
+  psq::PushArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  if (peer) { pa.pc = peer_ctx(peer); pa.on = 1; }
   c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, ftotal ? ftotal : c.ws.ftotal,
-                   st);
+                   peer ? &pa : nullptr, st);
   return check_launch();
 }
 
 int psqrt_carry_filter(const double* totals, int rank, int64_t batch, int nx, const double* m0, const double* L0,
-                       double* carry_m, double* carry_L, void* stream) {
+                       double* carry_m, double* carry_L, const psqrt_peer* peer, void* stream) {
   const LaunchN* ln = table_for(nx);
   if (!ln) return PSQRT_EUNSUPPORTED;
-  if (rank < 0 || batch <= 0 || !m0 || !L0 || !carry_m || !carry_L || (rank > 0 && !totals)) return PSQRT_EINVAL;
-  ln->carry_filter(totals, rank, batch, m0, L0, carry_m, carry_L, (cudaStream_t)stream);
+  if (rank < 0 || batch <= 0 || batch > 65535 || !m0 || !L0 || !carry_m || !carry_L) return PSQRT_EINVAL;
+  psq::PeerCtx pc;
+  if (peer) {
+    if (!peer_ok(peer, batch) || peer->rank != rank || peer->payload != ln->nf_filter) return PSQRT_EINVAL;
+    pc = peer_ctx(peer);
+  } else if (rank > 0 && !totals) {
+    return PSQRT_EINVAL;
+  }
+  ln->carry_filter(totals, rank, batch, m0, L0, carry_m, carry_L, peer ? &pc : nullptr, (cudaStream_t)stream);
   return check_launch();
 }
 
 int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carry_m, const double* carry_L, int nx,
                        int ny, int64_t T, int64_t batch, int chunk_len, double* fm, double* fL, double* ell,
-                       double* stotal, void* ws, size_t ws_bytes, void* stream) {
+                       double* stotal, void* ws, size_t ws_bytes, const psqrt_peer* peer, void* stream) {
   if (!ssm_ok(ssm, true) || !y || ny <= 0 || !carry_m || !carry_L || !fm || !fL) return PSQRT_EINVAL;
+  if (peer && (!peer_ok(peer, batch) || !stotal)) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
+  if (peer && peer->payload != c.ln->nf_smoother + nx + (int64_t)nx * nx) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
   const int smooth = stotal != nullptr;
@@ -285,8 +280,16 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
                       carry_L, c.ws.chunk_own, c.ws.chunk_pref, c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf,
                       c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.fpack, st);
   if (smooth) {
+    psq::PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (peer) {
+      // the smoothing total travels with the shard's last filtered state (the last rank's is the terminal element)
+      pa.pc = peer_ctx(peer); pa.on = 1;
+      pa.x1 = fm + (size_t)T * nx; pa.s1 = (long long)(T + 1) * nx; pa.n1 = nx;
+      pa.x2 = fL + (size_t)T * nx * nx; pa.s2 = (long long)(T + 1) * nx * nx; pa.n2 = nx * nx;
+    }
     c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, stotal,
-                     ell ? c.ws.ell_part : nullptr, ell, st);
+                     ell ? c.ws.ell_part : nullptr, ell, peer ? &pa : nullptr, st);
   } else if (ell) {
     psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
   }
@@ -294,20 +297,45 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
 }
 
 int psqrt_carry_smoother(const double* totals, int rank, int n_ranks, int64_t batch, int nx, const double* mT,
-                         const double* LT, double* carry_m, double* carry_L, void* stream) {
+                         const double* LT, double* carry_m, double* carry_L, const psqrt_peer* peer, void* stream) {
   const LaunchN* ln = table_for(nx);
   if (!ln) return PSQRT_EUNSUPPORTED;
-  if (rank < 0 || rank >= n_ranks || batch <= 0 || !mT || !LT || !carry_m || !carry_L ||
-      (rank + 1 < n_ranks && !totals))
+  if (rank < 0 || rank >= n_ranks || batch <= 0 || batch > 65535 || !carry_m || !carry_L) return PSQRT_EINVAL;
+  psq::PeerCtx pc;
+  if (peer) {
+    if (!peer_ok(peer, batch) || peer->rank != rank || peer->n_ranks != n_ranks ||
+        peer->payload != ln->nf_smoother + nx + (int64_t)nx * nx)
+      return PSQRT_EINVAL;
+    pc = peer_ctx(peer);
+  } else if (!mT || !LT || (rank + 1 < n_ranks && !totals)) {
     return PSQRT_EINVAL;
-  ln->carry_smoother(totals, rank, n_ranks, batch, mT, LT, carry_m, carry_L, (cudaStream_t)stream);
+  }
+  ln->carry_smoother(totals, rank, n_ranks, batch, mT, LT, carry_m, carry_L, peer ? &pc : nullptr,
+                     (cudaStream_t)stream);
   return check_launch();
+}
+
+int64_t psqrt_peer_layout(int nx, int n_ranks, int64_t batch, psqrt_peer* f, psqrt_peer* s) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln || n_ranks <= 0 || batch <= 0 || !f || !s) return 0;
+  int64_t off = 0;
+  auto phase = [&](psqrt_peer* p, int64_t payload) {
+    p->n_ranks = n_ranks; p->batch = batch; p->payload = payload; p->slot = batch * payload;
+    p->flags_off = off; off += (int64_t)n_ranks * batch;
+    p->ctr_off = off; off += batch;
+    off = (off + 1) & ~(int64_t)1;
+    p->data_off = off; off += 2 * (int64_t)n_ranks * p->slot;
+    off = (off + 1) & ~(int64_t)1;
+  };
+  phase(f, ln->nf_filter);
+  phase(s, ln->nf_smoother + nx + (int64_t)nx * nx);
+  return off;
 }
 
 int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
                          double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
-  (void)fm; (void)fL;  // psqrt_filter_apply left the packed filtered states in the workspace
+  (void)fm; (void)fL;  // identify the pass: psqrt_filter_apply left their packed copy in the workspace (psqrt.h)
   if (!ssm_ok(ssm, false) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
@@ -327,11 +355,11 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
-  rc = psqrt_filter_reduce(ssm, y, nx, ny, T, batch, chunk_len, c.ws.ftotal, ws, ws_bytes, stream);
+  rc = psqrt_filter_reduce(ssm, y, nx, ny, T, batch, chunk_len, c.ws.ftotal, ws, ws_bytes, nullptr, stream);
   if (rc) return rc;
   const bool smooth = sm != nullptr;
   rc = psqrt_filter_apply(ssm, y, m0, L0, nx, ny, T, batch, chunk_len, fm, fL, ell, smooth ? c.ws.stotal : nullptr, ws,
-                          ws_bytes, stream);
+                          ws_bytes, nullptr, stream);
   if (rc || !smooth) return rc;
   // terminal carry = filtered state at index T of every sequence
   SSMArgs a = make_args(ssm, nullptr, 0, T);
@@ -355,7 +383,7 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
   c.ln->smooth_reduce(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, fm, fL,
                       c.ws.chunk_suf, c.ws.warp_stot, c.ws.counter_s, c.ws.fpack, st);
   c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
-                   st);
+                   nullptr, st);
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
                      fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,
                      (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL, 1,
@@ -385,7 +413,7 @@ int psqrt_filter_scan(const double* A, const double* b, const double* U, const d
   cudaStream_t st = (cudaStream_t)stream;
   c.ln->escan_filter_reduce(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
                             c.ws.warp_tot, c.ws.counter_f, st);
-  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, c.ws.ftotal, st);
+  c.ln->mid_filter(c.ws.warp_tot, c.plan.n_warps, batch, c.ws.group_f, c.ws.counter_f, c.ws.ftotal, nullptr, st);
   c.ln->escan_filter_apply(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
                            c.ws.warp_tot, c.ws.group_f, means, chols, st);
   return check_launch();
@@ -410,7 +438,7 @@ int psqrt_smoother_scan(const double* g, const double* E, const double* D, int n
   c.ln->escan_smooth_reduce(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
                             c.ws.counter_s, st);
   c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, c.ws.stotal, nullptr, nullptr,
-                   st);
+                   nullptr, st);
   c.ln->escan_smooth_apply(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,
                            c.ws.group_s, means, chols, st);
   return check_launch();
@@ -451,25 +479,6 @@ int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t b
   if (!ln) return PSQRT_EUNSUPPORTED;
   if (!A || !L || cols <= 0 || batch <= 0) return PSQRT_EINVAL;
   ln->tria(A, L, cols, batch, (cudaStream_t)stream);
-  return check_launch();
-}
-
-int psqrt_peer_push(const double* src0, int64_t count0, int64_t dst_off0, const double* src1, int64_t count1,
-                    int64_t dst_off1, const double* src2, int64_t count2, int64_t dst_off2,
-                    double* const* peer_bufs, unsigned long long* const* peer_flags, int rank, int n_ranks,
-                    const unsigned long long* epoch_ctr, void* stream) {
-  if (!peer_bufs || !peer_flags || !epoch_ctr || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return PSQRT_EINVAL;
-  if ((count0 > 0 && !src0) || (count1 > 0 && !src1) || (count2 > 0 && !src2)) return PSQRT_EINVAL;
-  psq::PushSeg a{src0, count0, dst_off0}, b{src1, count1, dst_off1}, c{src2, count2, dst_off2};
-  psq::k_peer_push<<<n_ranks, 128, 0, (cudaStream_t)stream>>>(a, b, c, peer_bufs, peer_flags, rank, epoch_ctr);
-  return check_launch();
-}
-
-int psqrt_peer_wait(const unsigned long long* flags, int first, int last, unsigned long long* epoch_ctr,
-                    void* stream) {
-  if (!flags || !epoch_ctr || first < 0 || last - first + 1 > 1024) return PSQRT_EINVAL;
-  const int n = last >= first ? last - first + 1 : 1;   // always launched: it also advances the epoch
-  psq::k_peer_wait<<<1, n, 0, (cudaStream_t)stream>>>(flags, first, last, epoch_ctr);
   return check_launch();
 }
 

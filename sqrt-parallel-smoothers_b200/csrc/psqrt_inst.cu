@@ -21,7 +21,9 @@ const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
 }
 #else
 #include "psqrt_kernels.cuh"
+#if !PSQ_MID2
 #include "psqrt_coop.cuh"
+#endif
 
 #include <stdlib.h>
 #include <string.h>
@@ -159,38 +161,81 @@ const LaunchNY* for_ny(int ny) {
   }
 }
 
-inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31) / 32), (unsigned)B, 1); }
-
-// The filtering mid-level scan runs one half-warp per combine (psqrt_coop.cuh) for nx >= 5, where the
-// one-thread-per-combine kernel spills; PSQRT_MID_SCAN=thread selects k_mid_scan everywhere (A/B timing).
-constexpr bool kCoopMid = (PSQ_N >= 5);
-inline bool use_coop_mid() {
-  static const bool on = [] {
-    const char* e = getenv("PSQRT_MID_SCAN");
-    return !(e && strcmp(e, "thread") == 0);
-  }();
-  return kCoopMid && on;
+#if PSQ_MID2
+// Mid-level scans in the sub-warp form (psqrt_coop2.cuh): one lane group per combine, dense elements in shared memory.
+template <class OP, int NF, bool REV>
+void launch_mid2(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                 const double* ell_part, double* ell_out, const PushArgs* push, cudaStream_t st) {
+  constexpr int IT = MidCfg<N>::IT;
+  constexpr size_t smem = mid2_smem_bytes<OP, NF, IT>();
+  static_assert(smem <= 227 * 1024, "mid scan: shared memory budget");
+  auto kern = k_mid_scan2<OP, NF, IT, REV>;
+  if (smem > 48 * 1024)  // per device, so not cached per process
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long Gc = (M + IT - 1) / IT;
+  PushArgs pa;
+  if (push) pa = *push; else memset(&pa, 0, sizeof(pa));
+  kern<<<dim3((unsigned)Gc, (unsigned)B, 1), IT * OP::G, smem, st>>>(items, M, groups, Gc, counter, total, ell_part,
+                                                                     ell_out, pa);
 }
 void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
-                cudaStream_t st) {
+                const PushArgs* push, cudaStream_t st) {
+  launch_mid2<CoopF2<N>, FElem<N>::NF, false>(items, M, B, groups, counter, total, nullptr, nullptr, push, st);
+}
+void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                const double* ell_part, double* ell_out, const PushArgs* push, cudaStream_t st) {
+  launch_mid2<CoopS2<N>, SElem<N>::NF, true>(items, M, B, groups, counter, total, ell_part, ell_out, push, st);
+}
+// Time-shard carries: log-depth scan of the shard totals after a seed element built from the prior / terminal state.
+template <class OP, int NF>
+void launch_carry(const double* totals, int first, int step, int count, long long B, const double* m, const double* L,
+                  double* cm, double* cL, const PeerCtx* pc, int seed_rank, long long mext, long long Lext,
+                  cudaStream_t st) {
+  constexpr size_t smem = carry_smem_bytes<OP, NF>();
+  static_assert(smem <= 227 * 1024, "carry scan: shared memory budget");
+  auto kern = k_carry_scan<OP, NF, N>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  PeerCtx p;
+  if (pc) p = *pc; else memset(&p, 0, sizeof(p));
+  const long long payload = pc ? pc->payload : NF;
+  kern<<<(unsigned)B, kCarryIT * OP::G, smem, st>>>(totals, first, step, count, B, payload, m, L, (long long)N,
+                                                    (long long)N * N, cm, cL, p, pc ? 1 : 0, seed_rank, mext, Lext);
+}
+void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
+                  double* cL, const PeerCtx* pc, cudaStream_t st) {
+  launch_carry<CoopF2<N>, FElem<N>::NF>(totals, 0, 1, rank, B, m0, L0, cm, cL, pc, -1, 0, 0, st);
+}
+void carry_smoother(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
+                    double* cm, double* cL, const PeerCtx* pc, cudaStream_t st) {
+  // with a peer exchange the terminal state is the last rank's published last filtered state
+  launch_carry<CoopS2<N>, SElem<N>::NF>(totals, R - 1, -1, R - 1 - rank, B, mT, LT, cm, cL, pc, pc ? R - 1 : -1,
+                                        SElem<N>::NF, SElem<N>::NF + N, st);
+}
+#else
+inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31) / 32), (unsigned)B, 1); }
+
+// round-1 mid scans: the filtering one runs one half-warp per combine (psqrt_coop.cuh) for nx >= 5, where the
+// one-thread-per-combine kernel spills
+constexpr bool kCoopMid = (PSQ_N >= 5);
+void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                const PushArgs*, cudaStream_t st) {
   if constexpr (kCoopMid) {
-    if (use_coop_mid()) {
-      constexpr size_t smem = coop_smem_bytes<N>();
-      static_assert(smem <= 227 * 1024, "cooperative mid scan: shared memory budget");
-      if (smem > 48 * 1024)  // per device, so not cached per process
-        cudaFuncSetAttribute(k_mid_scan_coop<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k_mid_scan_coop<N><<<mid_grid(M, B), 32 * kCoopWarps, smem, st>>>(items, M, groups, (M + 31) / 32, counter, total);
-      return;
-    }
+    constexpr size_t smem = coop_smem_bytes<N>();
+    static_assert(smem <= 227 * 1024, "cooperative mid scan: shared memory budget");
+    if (smem > 48 * 1024)  // per device, so not cached per process
+      cudaFuncSetAttribute(k_mid_scan_coop<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_mid_scan_coop<N><<<mid_grid(M, B), 32 * kCoopWarps, smem, st>>>(items, M, groups, (M + 31) / 32, counter, total);
+    return;
   }
   k_mid_scan<FElem<N>, false><<<mid_grid(M, B), 32 * Split<FElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32,
                                                                                  counter, total, nullptr, nullptr);
 }
 void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
-                const double* ell_part, double* ell_out, cudaStream_t st) {
+                const double* ell_part, double* ell_out, const PushArgs*, cudaStream_t st) {
   k_mid_scan<SElem<N>, true><<<mid_grid(M, B), 32 * Split<SElem<N>>::R, 0, st>>>(items, M, groups, (M + 31) / 32, counter, total, ell_part,
                                                           ell_out);
 }
+#endif
 void smooth_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                    const double* fm, const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter,
                    double* fpack, cudaStream_t st) {
@@ -226,14 +271,16 @@ void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, lon
   smooth_apply_t(SrcPtr{a}, T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm, sL,
                  write_terminal, st);
 }
+#if !PSQ_MID2
 void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
-                  double* cL, cudaStream_t st) {
+                  double* cL, const PeerCtx*, cudaStream_t st) {
   k_carry_filter<N><<<blocks_for(B, 32), 32, 0, st>>>(totals, rank, B, m0, L0, cm, cL);
 }
 void carry_smoother(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
-                    double* cm, double* cL, cudaStream_t st) {
+                    double* cm, double* cL, const PeerCtx*, cudaStream_t st) {
   k_carry_smoother<N><<<blocks_for(B, 32), 32, 0, st>>>(totals, rank, R, B, mT, LT, cm, cL);
 }
+#endif
 void smoother_elements(const SSMArgs& a, long long T, long long B, const double* fm, const double* fL, double* g,
                        double* E, double* D, cudaStream_t st) {
   k_smoother_elements<N><<<blocks_for((T + 1) * B, 128), 128, 0, st>>>(a, T, B, fm, fL, g, E, D);

@@ -2,7 +2,8 @@
 //
 // Time is cut into P chunks of K consecutive steps, one chunk per thread, 32 chunks per warp.
 //   K1 filter_reduce   : per chunk, the chunk summary (A,b,U,eta,Z) by the collapsed combine
-//                        (psq::filter_reduce_step); warp-level Kogge-Stone scan of the 32
+//                        (psq::filter_reduce_step; also stores the summary with its last step predict-only,
+//                        from which K3 builds the chunk's smoothing total); warp-level Kogge-Stone scan of the 32
 //                        summaries (generic combine, parsmooth/parallel/_operators.py:43-77);
 //                        writes the in-warp exclusive prefix per chunk and one total per warp.
 //   K2 mid_scan<FElem> : one CTA per sequence scans the warp totals (exclusive), emits the
@@ -22,6 +23,7 @@
 
 #include "psqrt_math.cuh"
 #include "psqrt_async.cuh"
+#include "psqrt_coop2.cuh"
 
 namespace psq {
 
@@ -301,7 +303,7 @@ k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
   if (c == 0) counter[seq] = 0u;  // arms the ticket of the mid-level scan that follows
-  FElem<N> acc;
+  FAcc<N> acc;
   acc.set_identity();
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
@@ -310,6 +312,7 @@ k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
 #pragma unroll
   for (int d = 0; d < kYDepth; ++d) yring.issue(d, k0 + d < k1, src.yp(seq, k0 + d), 1);
   int slot = 0;
+  double* const own = chunk_own + seq * FElem<N>::NF * Ppad + c;
 #pragma unroll 1
   for (long long k = k0; k < k1; ++k) {
     double ycur[NY];
@@ -319,10 +322,32 @@ k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
     yring.issue(slot, k + kYDepth < k1, src.yp(seq, k + kYDepth), 1);
     slot = (slot + 1 == kYDepth) ? 0 : slot + 1;
     const auto p = src.at(seq, k);
-    filter_reduce_step<N, NY>(acc, WithY<decltype(p), NY>{p, ycur});
+    const bool last = (k + 1 == k1);
+    filter_reduce_step<N, NY>(
+        acc, WithY<decltype(p), NY>{p, ycur},
+        [&](const double (&FA)[N][N], const double (&mp)[N], const double (&Np)[N][2 * N], const FAcc<N>& a) {
+          // the chunk's summary with its LAST step predict-only, in FElem order (A, b, U, eta, Z): K3 derives the
+          // chunk's smoothing total from it (psq::chunk_smoothing_total)
+          if (last) {
+            constexpr int TRI = FElem<N>::TRI;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              own[(N * N + i) * Ppad] = mp[i];
+              own[(N * N + N + TRI + i) * Ppad] = a.eta[i];
+#pragma unroll
+              for (int j = 0; j < N; ++j) own[(i * N + j) * Ppad] = FA[i][j];
+#pragma unroll
+              for (int j = 0; j <= i; ++j) {
+                own[(N * N + N + i * (i + 1) / 2 + j) * Ppad] = Np[i][j];
+                own[(N * N + 2 * N + TRI + i * (i + 1) / 2 + j) * Ppad] = a.Z[i * (i + 1) / 2 + j];
+              }
+            }
+          }
+        });
   }
-  soa_store(chunk_own, seq, Ppad, c, acc);  // K3 derives the chunk's smoothing total from it
-  FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(acc, lane);
+  FElem<N> own_e;
+  acc.to_elem(own_e);
+  FElem<N> incl = warp_scan_inclusive<FElem<N>, false>(own_e, lane);
   FElem<N> excl = warp_exclusive_from_inclusive<FElem<N>, false>(incl, lane);
   soa_store(chunk_pref, seq, Ppad, c, excl);
   if (lane == 31) soa_store(warp_tot, seq, Ppad / 32, c / 32, incl);
@@ -516,9 +541,10 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   // copies: code that runs once per kernel is paid for in cold instruction fetches (see k_mid_scan).
 #pragma unroll 1
   for (int lvl = 0; lvl < 3; ++lvl) {
+    constexpr int IT = MidCfg<N>::IT;   // warps per group of the mid-level scan
     const double* buf = (lvl == 0) ? group_pref : (lvl == 1) ? warp_pref : chunk_pref;
-    const long long n_items = (lvl == 0) ? (Mw + 31) / 32 : (lvl == 1) ? Mw : Ppad;
-    const long long idx = (lvl == 0) ? c / 1024 : (lvl == 1) ? c / 32 : c;
+    const long long n_items = (lvl == 0) ? (Mw + IT - 1) / IT : (lvl == 1) ? Mw : Ppad;
+    const long long idx = (lvl == 0) ? c / (32 * IT) : (lvl == 1) ? c / 32 : c;
     FElem<N> e;
     soa_load(buf, seq, n_items, idx, e);
     filtering_apply<N>(x, e);
@@ -650,9 +676,10 @@ k_smooth_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
     if (write_terminal && k1 == T) store_gauss_dense<N>(smS + T * N, sLS + T * N * N, xs);
 #pragma unroll 1
     for (int lvl = 0; lvl < 3; ++lvl) {   // terminal state pushed through the three exclusive suffixes
+      constexpr int IT = MidCfg<N>::IT;
       const double* buf = (lvl == 0) ? group_suf : (lvl == 1) ? warp_suf : chunk_suf;
-      const long long n_items = (lvl == 0) ? (Mw + 31) / 32 : (lvl == 1) ? Mw : Ppad;
-      const long long idx = (lvl == 0) ? (Mw - 1 - c / 32) / 32 : (lvl == 1) ? c / 32 : c;  // groups: scan (reverse) order
+      const long long n_items = (lvl == 0) ? (Mw + IT - 1) / IT : (lvl == 1) ? Mw : Ppad;
+      const long long idx = (lvl == 0) ? (Mw - 1 - c / 32) / IT : (lvl == 1) ? c / 32 : c;  // groups: scan (reverse) order
       SElem<N> e;
       soa_load(buf, seq, n_items, idx, e);
       smoothing_apply<N>(xs, e);
@@ -875,7 +902,7 @@ k_escan_filter_apply(const double* A, const double* b, const double* U, const do
     }
   }
   FElem<N> e;
-  soa_load(group_pref, seq, (Ppad / 32 + 31) / 32, c / 1024, e);
+  soa_load(group_pref, seq, (Ppad / 32 + MidCfg<N>::IT - 1) / MidCfg<N>::IT, c / (32 * MidCfg<N>::IT), e);
   filtering_apply<N>(x, e);
   soa_load(warp_pref, seq, Ppad / 32, c / 32, e);
   filtering_apply<N>(x, e);
@@ -935,7 +962,7 @@ k_escan_smooth_apply(const double* g, const double* E, const double* D, long lon
     }
   }
   SElem<N> e;
-  soa_load(group_suf, seq, (Ppad / 32 + 31) / 32, (Ppad / 32 - 1 - c / 32) / 32, e);
+  soa_load(group_suf, seq, (Ppad / 32 + MidCfg<N>::IT - 1) / MidCfg<N>::IT, (Ppad / 32 - 1 - c / 32) / MidCfg<N>::IT, e);
   smoothing_apply<N>(x, e);
   soa_load(warp_suf, seq, Ppad / 32, c / 32, e);
   smoothing_apply<N>(x, e);

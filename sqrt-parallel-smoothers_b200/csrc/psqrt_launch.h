@@ -7,6 +7,8 @@
 namespace psq {
 
 struct SSMArgs;
+struct PushArgs;
+struct PeerCtx;
 
 // host mirrors of a time- and batch-invariant model (all six non-null) or nullptr entries
 struct HostModel {
@@ -31,10 +33,11 @@ struct LaunchN {
   int n;
   int nf_filter, nf_smoother, nf_state;
   const LaunchNY* (*for_ny)(int ny);
+  // push != nullptr: the CTA that finishes the scan publishes the total in every rank's exchange buffer (psqrt_coop2.cuh)
   void (*mid_filter)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
-                     cudaStream_t);
+                     const PushArgs* push, cudaStream_t);
   void (*mid_smooth)(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
-                     const double* ell_part, double* ell_out, cudaStream_t);
+                     const double* ell_part, double* ell_out, const PushArgs* push, cudaStream_t);
   void (*smooth_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, const double* fm,
                         const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, double* fpack,
                         cudaStream_t);
@@ -42,10 +45,11 @@ struct LaunchN {
                        const double* carry_m, const double* carry_L, long long cms, long long cLs,
                        const double* chunk_suf, const double* warp_suf, const double* group_suf, const double* fpack,
                        double* sm, double* sL, int write_terminal, cudaStream_t);
+  // pc != nullptr: wait for all ranks' pass number, then fold the totals out of the local exchange buffer
   void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
-                       double* cL, cudaStream_t);
+                       double* cL, const PeerCtx* pc, cudaStream_t);
   void (*carry_smoother)(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
-                         double* cm, double* cL, cudaStream_t);
+                         double* cm, double* cL, const PeerCtx* pc, cudaStream_t);
   void (*smoother_elements)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* g,
                             double* E, double* D, cudaStream_t);
   void (*escan_filter_reduce)(const double* A, const double* b, const double* U, const double* eta, const double* Z,

@@ -326,9 +326,66 @@ PSQ_HD void psi11_inv_diag(const double (&M2)[NY + N][N + NY], double (&inv)[NY]
 // ever forming e_k: the combine _operators.py:58-77 collapses, for a rank-NY information
 // factor Z_k, to one square-root Kalman predict+update on (b, U), two N x N products on A and
 // a rank-NY append on Z.  (Equality with the generic combine is tested against the oracle.)
+//
+// The running summary keeps ANY dense square root Y of U U^T (like kalman_step_dense): only the NY
+// reflectors of the update that produce Psi11 / Psi21 are loop-carried; the N - 1 reflectors that would
+// make the factor lower triangular are applied once, at the end of the chunk (FAcc::to_elem).
+//
+// `pre` is called once per step with the PREDICT-ONLY summary of the step (F A, F b + bq,
+// tria([F Y | Q]), eta, Z -- i.e. acc (x) (F, bq, Q, 0, 0)).  Sweep 1 stores that of the LAST step of a
+// chunk: the chunk's smoothing total is built from it (chunk_smoothing_total), so that -- like the
+// per-step elements of _smoothing.py:76-85 -- only PREDICTED factors are ever inverted.
 // ---------------------------------------------------------------------------------------
-template <int N, int NY, class P>
-PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
+template <int N>
+struct FAcc {
+  static constexpr int TRI = N * (N + 1) / 2;
+  double A[N][N], b[N], Y[N][N], eta[N], Z[TRI];
+  PSQ_HD double& Zc(int i, int j) { return Z[i * (i + 1) / 2 + j]; }
+  PSQ_HD void set_identity() {
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      b[i] = 0.0;
+      eta[i] = 0.0;
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) {
+        A[i][j] = (i == j) ? 1.0 : 0.0;
+        Y[i][j] = 0.0;
+      }
+    }
+    PSQ_UNROLL
+    for (int f = 0; f < TRI; ++f) Z[f] = 0.0;
+  }
+  // packed element with U = tria(Y)
+  PSQ_HD void to_elem(FElem<N>& e) const {
+    double Yt[N][N];
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i) {
+      e.b(i) = b[i];
+      e.eta(i) = eta[i];
+      PSQ_UNROLL
+      for (int j = 0; j < N; ++j) {
+        e.A(i, j) = A[i][j];
+        Yt[i][j] = Y[i][j];
+      }
+    }
+    house_rows<N, N, N - 1>(Yt);
+    PSQ_UNROLL
+    for (int i = 0; i < N; ++i)
+      PSQ_UNROLL
+      for (int j = 0; j <= i; ++j) {
+        e.U(i, j) = Yt[i][j];
+        e.Z(i, j) = Z[i * (i + 1) / 2 + j];
+      }
+  }
+};
+
+struct NoPre {
+  template <class... Args>
+  PSQ_HD void operator()(Args&&...) const {}
+};
+
+template <int N, int NY, class P, class PRE>
+PSQ_HD void filter_reduce_step(FAcc<N>& acc, const P& p, PRE&& pre) {
   double F[N][N];
   PSQ_UNROLL
   for (int i = 0; i < N; ++i)
@@ -340,25 +397,45 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
   for (int i = 0; i < N; ++i) {
     double s = p.fb(i);
     PSQ_UNROLL
-    for (int k = 0; k < N; ++k) s = fma(F[i][k], acc.b(k), s);
+    for (int k = 0; k < N; ++k) s = fma(F[i][k], acc.b[k], s);
     mp[i] = s;
     PSQ_UNROLL
     for (int j = 0; j < N; ++j) {
       double a = 0.0;
       PSQ_UNROLL
-      for (int k = 0; k < N; ++k) a = fma(F[i][k], acc.A(k, j), a);
+      for (int k = 0; k < N; ++k) a = fma(F[i][k], acc.A[k][j], a);
       FA[i][j] = a;
       double u = 0.0;
       PSQ_UNROLL
-      for (int k = j; k < N; ++k) u = fma(F[i][k], acc.U(k, j), u);
+      for (int k = 0; k < N; ++k) u = fma(F[i][k], acc.Y[k][j], u);
       M1[i][j] = u;
       M1[i][N + j] = (j <= i) ? p.template fQ<N>(i, j) : 0.0;  // cholQ is lower triangular (psqrt.h)
     }
   }
-  house_rows<N, 2 * N, N, N>(M1);  // predicted factor = tria([F U | Q]); Q's triangle shortens every reflector
+  house_rows<N, 2 * N, N, N>(M1);  // predicted factor = tria([F Y | Q]); Q's triangle shortens every reflector
+  pre(FA, mp, M1, acc);
 
+  // [[H Np, R], [Np, 0]]: only the NY reflectors that give Psi11 / Psi21; rows >= NY, columns >= NY then hold a
+  // dense square root of the posterior covariance                                    _filtering.py:126-131
   double M2[NY + N][N + NY];
-  build_update<N, NY>(p, [&](int i, int j) { return M1[i][j]; }, M2);
+  PSQ_UNROLL
+  for (int a = 0; a < NY; ++a) {
+    PSQ_UNROLL
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      PSQ_UNROLL
+      for (int k = j; k < N; ++k) s = fma(p.template fH<N>(a, k), M1[k][j], s);
+      M2[a][j] = s;
+    }
+    PSQ_UNROLL
+    for (int q = 0; q < NY; ++q) M2[a][N + q] = p.template fR<NY>(a, q);
+  }
+  PSQ_UNROLL
+  for (int i = 0; i < N; ++i) {
+    PSQ_UNROLL
+    for (int j = 0; j < N + NY; ++j) M2[NY + i][j] = (j <= i) ? M1[i][j] : 0.0;
+  }
+  house_rows<NY + N, N + NY, NY>(M2);
   double inv[NY];
   psi11_inv_diag<N, NY>(M2, inv);
 
@@ -385,26 +462,25 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
       V[a][j] = s * inv[a];
     }
   }
-  // A <- FA - Psi21 V ; b <- mp + Psi21 rr ; eta <- eta + V^T rr ; U <- posterior factor
+  // A <- FA - Psi21 V ; b <- mp + Psi21 rr ; eta <- eta + V^T rr ; Y <- posterior factor
   PSQ_UNROLL
   for (int i = 0; i < N; ++i) {
     double bi = mp[i];
     PSQ_UNROLL
     for (int a = 0; a < NY; ++a) bi = fma(M2[NY + i][a], rr[a], bi);
-    acc.b(i) = bi;
-    double e = acc.eta(i);
+    acc.b[i] = bi;
+    double e = acc.eta[i];
     PSQ_UNROLL
     for (int a = 0; a < NY; ++a) e = fma(V[a][i], rr[a], e);
-    acc.eta(i) = e;
+    acc.eta[i] = e;
     PSQ_UNROLL
     for (int j = 0; j < N; ++j) {
       double s = FA[i][j];
       PSQ_UNROLL
       for (int a = 0; a < NY; ++a) s = fma(-M2[NY + i][a], V[a][j], s);
-      acc.A(i, j) = s;
+      acc.A[i][j] = s;
+      acc.Y[i][j] = M2[NY + i][NY + j];
     }
-    PSQ_UNROLL
-    for (int j = 0; j <= i; ++j) acc.U(i, j) = M2[NY + i][NY + j];
   }
   // Z <- tria([Z | V^T])
   double W[N][NY];
@@ -412,7 +488,7 @@ PSQ_HD void filter_reduce_step(FElem<N>& acc, const P& p) {
   for (int i = 0; i < N; ++i)
     PSQ_UNROLL
     for (int a = 0; a < NY; ++a) W[i][a] = V[a][i];
-  tria_append<N, NY>([&](int i, int j) -> double& { return acc.Z(i, j); }, W);
+  tria_append<N, NY>([&](int i, int j) -> double& { return acc.Zc(i, j); }, W);
 }
 
 // ---------------------------------------------------------------------------------------

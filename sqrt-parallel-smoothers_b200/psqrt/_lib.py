@@ -94,16 +94,43 @@ def _stream():
 
 
 _ws_cache = {}
+_ws_gen = {}
 WS_SLOT = 0   # staged calls of one pass must share a workspace; tests emulating several ranks on one GPU switch slots
 
 
-def workspace(nbytes: int, device: torch.device, slot: Optional[int] = None) -> torch.Tensor:
+def _ws_key(device: torch.device, slot: Optional[int] = None):
     slot = WS_SLOT if slot is None else slot
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    return (device.index if device.index is not None else torch.cuda.current_device(), slot)
+
+
+def workspace(nbytes: int, device: torch.device, slot: Optional[int] = None, *, writer: bool = True) -> torch.Tensor:
+    """Per-(device, slot) scratch buffer.  Every call that may overwrite it (`writer`) starts a new generation:
+    staged calls that read what an earlier stage left there (smoother_apply after filter_apply) check that no
+    other call used the buffer in between (see _stage_token / _check_stage)."""
+    key = _ws_key(device, slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
+    if writer:
+        _ws_gen[key] = _ws_gen.get(key, 0) + 1
+    return buf
+
+
+def _stage_token(device):
+    key = _ws_key(device)
+    return (key, _ws_gen.get(key, 0), _ws_cache[key].data_ptr())
+
+
+def _check_stage(token, what):
+    if token is None:
+        raise PsqrtError(f"{what}: the filtered trajectory must come from psqrt._lib.filter_apply of the same pass "
+                         f"(its workspace holds the packed filtered states this stage reads)")
+    key, gen, ptr = token
+    buf = _ws_cache.get(key)
+    if buf is None or buf.data_ptr() != ptr or _ws_gen.get(key, 0) != gen:
+        raise PsqrtError(f"{what}: the workspace of the matching filter_apply was reused or reallocated by another "
+                         f"psqrt call in between; run the stages of one pass back to back (or on separate WS_SLOTs)")
     return buf
 
 
@@ -124,12 +151,16 @@ def _require(nx: int, ny: int):
 
 
 class LinearizedSSM:
-    """Per-step linearised model (F, cholQ, b, H, cholR, c): each entry is a tensor whose leading
-    dims are [] (shared), [T] (per step) or [B, T] / [B] (per sequence).
+    """Per-step linearised model (F, cholQ, b, H, cholR, c).  Leading dims of each entry:
+    [] (shared by every step and sequence), [T] (per step, shared by the sequences), [B, T] (per sequence and
+    step) or [B, 1] (per sequence, time-invariant).  A single leading dim is ALWAYS time: a per-sequence
+    time-invariant entry must be given as [B, 1, ...] (a bare [B, ...] entry raises unless B == T, where it
+    cannot be told apart from a per-step entry and is read as one).
 
     `host`: optional {name: numpy array} mirrors of time-invariant entries (also picked up from a
-    `_psqrt_host` attribute on the tensors).  With mirrors for every entry of a fully shared model the
-    kernels take the model by value (constant-bank operands) instead of loading it per step."""
+    `_psqrt_host` attribute that psqrt.methods attaches to tensors it created from host data, as long as the
+    tensor has not been modified since).  With mirrors for every entry of a fully shared model the kernels take
+    the model by value (constant-bank operands) instead of loading it per step."""
 
     def __init__(self, F, cholQ, b, H=None, cholR=None, c=None, host=None):
         self.F, self.cholQ, self.b, self.H, self.cholR, self.c = F, cholQ, b, H, cholR, c
@@ -153,7 +184,8 @@ class LinearizedSSM:
                 pass
             elif len(lead) == 1:
                 if lead[0] != T:
-                    raise PsqrtError(f"{name}: leading dim {lead[0]} != T={T}")
+                    raise PsqrtError(f"{name}: leading dim {lead[0]} != T={T} (a single leading dim is time; "
+                                     f"per-sequence time-invariant entries must be [B, 1, ...])")
                 ts = size
             elif len(lead) == 2:
                 if lead[0] != batch or lead[1] not in (1, T):
@@ -165,7 +197,14 @@ class LinearizedSSM:
             setattr(s, name, _ptr(t).value)
             setattr(s, name + "_ts", ts)
             setattr(s, name + "_bs", bs)
-            h = self.host.get(name, getattr(getattr(self, name), "_psqrt_host", None))
+            h = self.host.get(name)
+            if h is None:
+                src = getattr(self, name)
+                mirror = getattr(src, "_psqrt_host", None)
+                # a mirror attached by psqrt.methods._t is a private copy stamped with the tensor's version
+                # counter: an in-place update of the device tensor since then makes it stale, and it is ignored
+                if mirror is not None and getattr(src, "_psqrt_host_version", None) == src._version:
+                    h = mirror
             if h is not None and len(lead) == 0:
                 h = np.ascontiguousarray(h, dtype=np.float64)
                 if h.shape == tuple(t.shape):
@@ -283,7 +322,7 @@ def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_l
     fL = torch.empty((B, T + 1, nx, nx), dtype=torch.float64, device=dev)
     ell = torch.empty((B,), dtype=torch.float64, device=dev) if loglik else None
     stotal = torch.empty((B, plan.nf_smoother), dtype=torch.float64, device=dev) if smooth else None
-    ws = workspace(lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len), dev)
+    ws = workspace(lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len), dev, writer=False)   # continues filter_reduce
     keep = []
     s = ssm.struct(T, B, keep)
     with torch.cuda.device(dev):
@@ -291,6 +330,7 @@ def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_l
                                     ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(ell), _ptr(stotal),
                                     ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), _stream())
     _check(rc, "psqrt_filter_apply")
+    fm._psqrt_stage = _stage_token(dev)    # smoother_apply reads the packed states this call left in the workspace
     return fm, fL, ell, stotal
 
 
@@ -306,11 +346,17 @@ def carry_smoother(totals, rank, n_ranks, mT, LT):
 
 
 def smoother_apply(ssm, fm, fL, carry_m, carry_L, *, write_terminal=True, chunk_len=0):
+    """Stage 5 of a time-sharded pass.  `fm`, `fL` must be the tensors returned by filter_apply of the SAME pass:
+    the kernel reads the packed copy of the filtered states that call left in the workspace (psqrt.h), and this
+    wrapper refuses to run if any other psqrt call touched that workspace in between."""
     lib = load()
     B, Tp1, nx = fm.shape
     T = Tp1 - 1
     sm, sL = torch.empty_like(fm), torch.empty_like(fL)
-    ws = workspace(lib.psqrt_workspace_bytes(0, nx, 0, T, B, chunk_len), fm.device)
+    ws = _check_stage(getattr(fm, "_psqrt_stage", None), "smoother_apply")
+    if ws.numel() < lib.psqrt_workspace_bytes(0, nx, 0, T, B, chunk_len):
+        raise PsqrtError("smoother_apply: workspace smaller than this stage needs (different T / batch / chunk_len "
+                         "than the matching filter_apply?)")
     keep = []
     s = ssm.struct(T, B, keep)
     with torch.cuda.device(fm.device):

@@ -138,11 +138,22 @@ class TimeShardedSmoother:
 
     def _peer_exchange(self, B, nf_f, nf_s):
         if self._peer is None or self._peer.B != B:
+            err = None
             try:
-                self._peer = PeerExchange(self.world, self.rank, B, nf_f, nf_s, self.nx, self.device, self.group)
-            except Exception as e:            # no symmetric memory on this system: NCCL all-gathers instead
-                self.exchange, self.exchange_error = "nccl", repr(e)
+                peer = PeerExchange(self.world, self.rank, B, nf_f, nf_s, self.nx, self.device, self.group)
+            except Exception as e:            # no symmetric memory on this system
+                peer, err = None, repr(e)
+            # the ranks must agree: if the rendezvous failed anywhere, everybody uses the NCCL all-gathers
+            # (a rank spinning on a flag while another sits in an all-gather would hang the job)
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                import warnings
+                self.exchange, self.exchange_error = "nccl", err or "peer exchange unavailable on another rank"
+                warnings.warn(f"psqrt: exchange='peer' requested but not available ({self.exchange_error}); "
+                              f"using NCCL all-gathers")
                 return None
+            self._peer = peer
         return self._peer
 
     def filter_smoother(self, ssm, y, m0, L0, *, smooth: bool = True, loglik: bool = False):
@@ -154,7 +165,9 @@ class TimeShardedSmoother:
         B = y.shape[0]
         ftotal = ops.filter_reduce(ssm, y, self.nx, chunk_len=self.chunk_len)                 # [B, nf_filter]
         peer = None
-        if self.exchange == "peer":
+        # Slot reuse of the single-buffered peer exchange is ordered by the smoother exchange of the same pass
+        # (see PeerExchange); a filter-only pass has no such back-edge, so it takes the all-gather
+        if self.exchange == "peer" and smooth:
             nf_s = (3 * self.nx * self.nx + 3 * self.nx) // 2
             peer = self._peer_exchange(B, ftotal.shape[-1], nf_s)
         if peer is not None:
@@ -323,3 +336,50 @@ def iterated_smoothing_batched(observations, x0: MVNSqrt, transition_model, obse
         _, _, ell = filter_smoother_batched(*args, nominal, True)
         return nominal, ell
     return nominal
+
+
+def iterated_smoothing_batch_sharded(observations, x0: MVNSqrt, transition_model, observation_model,
+                                     linearization_method: Callable, init_nominal: Optional[MVNSqrt] = None,
+                                     n_iter: int = 10, return_loglikelihood: bool = True, group=None, smoother=None):
+    """BASELINE.json configs[4] across GPUs (notebooks/robustness_100runs.py:52-72 runs the 100 data sets one after
+    the other): `observations` [n_runs, T, ny] is the SAME array on every rank (or any per-run indexable); run i goes
+    to rank i % world (batch_indices), every rank smooths its share as ONE batch (iterated_smoothing_batched) and
+    there is no data-path collective -- only the per-run log-likelihoods are gathered at the end.
+
+    Returns (local_indices, local_nominal [n_local, T + 1, ...], ell_all [n_runs] or None); ell_all is identical on
+    every rank, in run order.  `smoother` replaces iterated_smoothing_batched (the CPU tests inject a NumPy stand-in
+    to exercise this host logic over gloo)."""
+    world, rank = _world(group)
+    n_runs = len(observations)
+    idx = batch_indices(n_runs, world, rank)
+    if smoother is None:
+        smoother = iterated_smoothing_batched
+    if len(idx) > 0:
+        obs_local = observations[idx] if hasattr(observations, "shape") else torch.stack([observations[i] for i in idx])
+        nominal = init_nominal
+        if nominal is not None and nominal.mean.dim() == 3 and nominal.mean.shape[0] == n_runs:   # per-run nominals
+            nominal = MVNSqrt(nominal.mean[idx], nominal.chol[idx])
+        out = smoother(obs_local, x0, transition_model, observation_model, linearization_method, nominal,
+                       n_iter=n_iter, return_loglikelihood=return_loglikelihood)
+        local_nominal, ell_local = out if return_loglikelihood else (out, None)
+    else:
+        local_nominal, ell_local = None, None
+    if not return_loglikelihood:
+        return idx, local_nominal, None
+    # gather of scalars: every rank contributes a fixed-size vector (ceil(n_runs / world) entries, NaN-padded)
+    per = (n_runs + world - 1) // world
+    if ell_local is not None:
+        dev, dtype = ell_local.device, ell_local.dtype
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        dtype = torch.float64
+    mine = torch.full((per,), float("nan"), dtype=dtype, device=dev)
+    if ell_local is not None:
+        mine[:len(idx)] = ell_local.reshape(-1)
+    gathered = _all_gather(mine, world, group)                  # [world, per]
+    ell_all = torch.empty((n_runs,), dtype=dtype, device=dev)
+    for r in range(world):
+        ids = batch_indices(n_runs, world, r)
+        if ids:
+            ell_all[ids] = gathered[r, :len(ids)]
+    return idx, local_nominal, ell_all

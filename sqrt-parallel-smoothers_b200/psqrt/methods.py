@@ -35,7 +35,8 @@ def _t(x, dev):
     host = np.asarray(x.detach().cpu().numpy() if torch.is_tensor(x) else x, dtype=np.float64)
     t = torch.as_tensor(host).to(dev)
     if host.size <= 4096:
-        t._psqrt_host = host
+        t._psqrt_host = np.array(host, dtype=np.float64, copy=True)   # private copy: the caller may reuse its array
+        t._psqrt_host_version = t._version                            # stale after any in-place update of t
     return t
 
 
@@ -79,6 +80,8 @@ def _lower(chol):
     if getattr(chol, "_psqrt_lower", False):
         return chol
     host = getattr(chol, "_psqrt_host", None)
+    if host is not None and getattr(chol, "_psqrt_host_version", None) != chol._version:
+        host = None
     if host is not None:
         if not np.any(np.triu(host, 1)):
             return chol

@@ -17,7 +17,8 @@ class _LinearBuiltin:
 
     def _M(self, like):
         t = torch.as_tensor(self.M, dtype=torch.float64).to(like.device)
-        t._psqrt_host = np.asarray(self.M.detach().cpu().numpy(), dtype=np.float64)   # host mirror (by-value path)
+        t._psqrt_host = np.array(self.M.detach().cpu().numpy(), dtype=np.float64, copy=True)   # host mirror (by-value path)
+        t._psqrt_host_version = t._version
         return t
 
     def extended(self, x: MVNSqrt, q: MVNSqrt):

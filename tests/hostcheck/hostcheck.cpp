@@ -60,9 +60,23 @@ int pass(const HSsm& a, long long T, int K, const double* m0, const double* L0, 
     FElem<N> lanes[32];
     for (int l = 0; l < 32; ++l) {
       long long c = w * 32 + l, k0 = c * K, k1 = std::min<long long>(T, k0 + K);
-      lanes[l].set_identity();
-      for (long long k = k0; k < k1; ++k) filter_reduce_step<N, NY>(lanes[l], sp(a, k));
-      chunk_own[c] = lanes[l];
+      FAcc<N> acc;
+      acc.set_identity();
+      for (long long k = k0; k < k1; ++k) {
+        const bool last = (k + 1 == k1);
+        filter_reduce_step<N, NY>(acc, sp(a, k), [&](const double (&FA)[N][N], const double (&mp)[N],
+                                                     const double (&Np)[N][2 * N], const FAcc<N>& s) {
+          if (!last) return;   // the summary with its last step predict-only (what k_filter_reduce stores)
+          FElem<N>& o = chunk_own[c];
+          for (int i = 0; i < N; ++i) {
+            o.b(i) = mp[i];
+            o.eta(i) = s.eta[i];
+            for (int j = 0; j < N; ++j) o.A(i, j) = FA[i][j];
+            for (int j = 0; j <= i; ++j) { o.U(i, j) = Np[i][j]; o.Z(i, j) = s.Z[i * (i + 1) / 2 + j]; }
+          }
+        });
+      }
+      acc.to_elem(lanes[l]);
     }
     ks_scan(lanes, false);
     for (int l = 0; l < 32; ++l) {

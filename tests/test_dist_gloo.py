@@ -138,3 +138,57 @@ def test_partition_helpers():
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
     deal = [pdist.batch_indices(100, 8, r) for r in range(8)]
     assert sorted(sum(deal, [])) == list(range(100)) and {len(d) for d in deal} == {12, 13}
+
+
+def _worker_batch(rank, world, port, n_runs, q):
+    for p in (HERE, os.path.join(os.path.dirname(HERE), "oracle"), os.path.join(os.path.dirname(HERE), "sqrt-parallel-smoothers_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        _setup(rank, world, port)
+        import psqrt
+        from psqrt import dist as pdist
+        ys_all, x0, tm, om = _batch_runs(n_runs)
+
+        def smoother(obs_local, _x0, _tm, _om, _lin, nominal, n_iter, return_loglikelihood):
+            # NumPy stand-in for iterated_smoothing_batched: the oracle, run by run
+            ms, Ls, ells = [], [], []
+            for y in obs_local.numpy():
+                res, ell = O.iterated_smoothing(y, x0, tm, om, O.extended, None, True,
+                                                criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)
+                ms.append(res.mean), Ls.append(res.chol), ells.append(ell)
+            out = psqrt.MVNSqrt(torch.as_tensor(np.stack(ms)), torch.as_tensor(np.stack(Ls)))
+            return (out, torch.as_tensor(np.array(ells))) if return_loglikelihood else out
+
+        idx, nominal, ell_all = pdist.iterated_smoothing_batch_sharded(
+            torch.as_tensor(ys_all), None, None, None, None, None, n_iter=2, return_loglikelihood=True,
+            smoother=smoother)
+        q.put((rank, idx, None if nominal is None else nominal.mean.numpy(), ell_all.numpy()))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        q.put((rank, "error", repr(e)))
+        raise
+
+
+def _batch_runs(n_runs, T=12):
+    ys, x0, tm, om = _bearings_oracle(T * n_runs)
+    return ys.reshape(n_runs, T, 2), x0, tm, om
+
+
+@pytest.mark.parametrize("n_runs", [5, 1])
+def test_batch_sharded_world2(n_runs):
+    """BASELINE.json configs[4]: independent runs dealt round-robin, no data-path collective, the per-run
+    log-likelihoods gathered in run order on every rank (also when a rank gets no run at all)."""
+    res = _run(_worker_batch, 2, n_runs)
+    ys_all, x0, tm, om = _batch_runs(n_runs)
+    expect = []
+    for y in ys_all:
+        r, ell = O.iterated_smoothing(y, x0, tm, om, O.extended, None, True, criterion=lambda i, *_: i < 2,
+                                      return_loglikelihood=True)
+        expect.append((r.mean, ell))
+    for rank, idx, means, ell_all in res:
+        assert idx == list(range(rank, n_runs, 2))
+        np.testing.assert_allclose(ell_all, [e for _, e in expect], rtol=1e-12)
+        for j, i in enumerate(idx):
+            np.testing.assert_allclose(means[j], expect[i][0], rtol=1e-12, atol=1e-14)

@@ -690,3 +690,70 @@ def test_full_size_properties():
     tr_f = (a[1] ** 2).sum((-1, -2))
     tr_s = (a[3] ** 2).sum((-1, -2))
     assert bool((tr_s <= tr_f * (1 + 1e-9)).all())
+
+
+@pytest.mark.parametrize("kind", ["cholR=0", "R*1e-6", "R*1e12", "Q*1e12", "Q*1e-12"])
+@pytest.mark.parametrize("n,ny,T,K", [(4, 2, 3000, 0), (4, 2, 200, 7), (3, 1, 64, 4), (5, 2, 1500, 9), (2, 2, 40, 5),
+                                      (8, 4, 300, 3)])
+def test_limit_cases(kind, n, ny, T, K):
+    """The reference's limit cases (tests/test_sequential_filter.py:105-184: no information R*1e12, (almost)
+    infinite information R*1e-6; tests/test_sequential_smoother.py:71-120: no / infinite process noise) plus an
+    exactly noise-free observation (cholR = 0: the FILTERED covariance is singular, only predicted factors may be
+    inverted, as parallel/_smoothing.py:76-85 does), through the whole CUDA pass against the oracle's parallel AND
+    sequential square-root smoothers."""
+    from psqrt import _lib
+    if kind == "cholR=0" and ny >= n:
+        pytest.skip("noise-free observation of the whole state")
+    case = lgssm_case(n, ny, T, seed=3 * n + ny)
+    if kind == "cholR=0":
+        case["cholR"] = np.zeros_like(case["cholR"])
+    elif kind == "R*1e-6":
+        case["cholR"] = 1e-3 * case["cholR"]
+    elif kind == "R*1e12":
+        case["cholR"] = 1e6 * case["cholR"]
+    elif kind == "Q*1e12":
+        case["cholQ"] = 1e6 * case["cholQ"]
+    elif kind == "Q*1e-12":
+        case["cholQ"] = 1e-6 * case["cholQ"]
+    fm, fL, sm, sL, ell = _lib.filter_smoother(_ssm(case), _g(case["ys"]), _g(case["m0"]), _g(case["L0"]),
+                                               smooth=True, loglik=True, chunk_len=K)
+    assert bool(torch.isfinite(sm).all()) and bool(torch.isfinite(sL).all())
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case)
+    tol = TOL if kind != "Q*1e-12" else 1e-7      # nearly deterministic dynamics: cond(P_pred) ~ 1e12
+    _check_traj("filtered", fm, fL, ofm, ofc, tol=tol)
+    _check_traj("smoothed", sm, sL, osm, osc, tol=tol)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)
+    if T <= 300:
+        tm, om = oracle_lgssm_models(case)
+        x0 = O.MVNSqrt(case["m0"], case["L0"])
+        sf = O.seq_filtering(case["ys"], x0, tm, om, O.extended, None)
+        ss = O.seq_smoothing(tm, sf, O.extended, None)
+        _check_traj("smoothed-vs-seq", sm, sL, ss.mean, ss.chol, tol=max(tol, 1e-8))
+
+
+@pytest.mark.parametrize("lin_name", ["extended", "cubature"])
+def test_bearings_full_size_pass(lin_name):
+    """BASELINE.json configs[1]/[2] at their own size (bearings-only coordinated turn, nx = 5, T = 1e5): one sqrt
+    parallel filter + smoother pass + log-likelihood through the public API against the oracle at the same nominal
+    trajectory (a smooth random walk around the notebooks' initial nominal, so every step linearises elsewhere)."""
+    import psqrt
+    T = 100_000
+    ys, m0, cholQ, cholR, (obs_f, trans_f), (oobs, otrans) = _bearings_setup(T)
+    lin, olin = getattr(psqrt.linearization, lin_name), getattr(O, lin_name)
+    rng = np.random.RandomState(5)
+    nom_m = np.array([-1.0, -1.0, 6.0, 4.0, 2.0]) + 0.02 * np.cumsum(rng.randn(T + 1, 5), 0) / np.sqrt(np.arange(1, T + 2))[:, None]
+    nom_L = 0.2 * (np.tril(rng.rand(T + 1, 5, 5)) + np.eye(5))
+    x0 = psqrt.MVNSqrt(_g(m0), _g(np.eye(5)))
+    tm = psqrt.FunctionalModel(trans_f, psqrt.MVNSqrt(_g(np.zeros(5)), _g(cholQ)))
+    om = psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(_g(np.zeros(2)), _g(cholR)))
+    nominal = psqrt.MVNSqrt(_g(nom_m), _g(nom_L))
+    filt, ell = psqrt.filtering(ys, x0, tm, om, lin, nominal, True, True)
+    smo = psqrt.filter_smoother(ys, x0, tm, om, lin, nominal, True)
+    otm = O.FunctionalModel(otrans, O.MVNSqrt(np.zeros(5), cholQ))
+    oom = O.FunctionalModel(oobs, O.MVNSqrt(np.zeros(2), cholR))
+    ox0, onom = O.MVNSqrt(m0, np.eye(5)), O.MVNSqrt(nom_m, nom_L)
+    ofilt, oell = O.filtering(ys, ox0, otm, oom, olin, onom, True, True)
+    osmo = O.smoothing(otm, ofilt, olin, onom, True)
+    _check_traj("filtered", filt.mean, filt.chol, ofilt.mean, ofilt.chol)
+    _check_traj("smoothed", smo.mean, smo.chol, osmo.mean, osmo.chol)
+    assert abs(ell.item() - oell) <= TOL_ELL * abs(oell)

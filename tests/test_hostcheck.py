@@ -135,3 +135,36 @@ def test_elements_and_loglik(hostcheck, n, ny):
         assert np.all(Z[:, :, ny:] == 0)                    # zero padding, _filtering.py:141-142
     oterms = O.sqrt_loglikelihood_terms(*lin, fm, fL, case["ys"])
     assert rel_err(terms, oterms) < 1e-11
+
+
+def _limit_case(kind, n, ny, T, seed):
+    """The reference's limit cases (tests/test_sequential_filter.py:105-184, test_sequential_smoother.py:71-120)
+    on the C1 recipe: noise-free / very informative / uninformative observations, (almost) deterministic or
+    very noisy dynamics."""
+    case = lgssm_case(n, ny, T, seed)
+    if kind == "cholR=0":            # noise-free observation: the filtered covariance is singular
+        case["cholR"] = np.zeros_like(case["cholR"])
+    elif kind == "R*1e-6":           # test_filter_infinite_info
+        case["cholR"] = 1e-3 * case["cholR"]
+    elif kind == "R*1e12":           # test_filter_no_info
+        case["cholR"] = 1e6 * case["cholR"]
+    elif kind == "Q*1e12":           # test_smooth_one_standard_vs_sqrt_infinite_noise
+        case["cholQ"] = 1e6 * case["cholQ"]
+    elif kind == "Q*1e-12":          # (almost) test_smooth_one_standard_vs_sqrt_no_noise
+        case["cholQ"] = 1e-6 * case["cholQ"]
+    return case
+
+
+@pytest.mark.parametrize("kind", ["cholR=0", "R*1e-6", "R*1e12", "Q*1e12", "Q*1e-12"])
+@pytest.mark.parametrize("n,ny,T,K", [(4, 2, 200, 7), (3, 1, 64, 4), (5, 2, 90, 9), (2, 2, 40, 5)])
+def test_pass_limit_cases(hostcheck, kind, n, ny, T, K):
+    if kind == "cholR=0" and ny >= n:
+        pytest.skip("noise-free observation of the whole state: the predicted covariance is Q, upstream divides too")
+    case = _limit_case(kind, n, ny, T, seed=3 * n + ny)
+    fm, fL, sm, sL, ell = run_pass(hostcheck, case, K)
+    ofm, ofc, osm, osc, oell = oracle_from_ssm(case, scan=O.sequential_scan if hasattr(O, "sequential_scan") else None)
+    tol = 1e-9 if kind != "Q*1e-12" else 1e-7
+    assert np.all(np.isfinite(sm)) and np.all(np.isfinite(sL))
+    assert rel_err(fm, ofm) < tol and rel_err(LLt(fL), LLt(ofc)) < tol
+    assert rel_err(sm, osm) < tol and rel_err(LLt(sL), LLt(osc)) < tol
+    assert abs(ell - oell) < 1e-8 * abs(oell)
