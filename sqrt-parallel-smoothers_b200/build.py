@@ -87,6 +87,43 @@ def _compile(args):
     return obj
 
 
+def build_xla_shim(verbose: bool = True):
+    """The XLA FFI shim (csrc/xla/xla_ffi_shim.cc: libpsqrt.so's whole-pass entry points as JAX custom calls) needs
+    jaxlib's headers (xla/ffi/api/ffi.h), which this image does not have: it is compiled into libpsqrt_xla.so only when
+    PSQRT_XLA_INCLUDE (or an importable jaxlib) provides them; otherwise the file is syntax-checked against psqrt.h."""
+    src = os.path.join(CSRC, "xla", "xla_ffi_shim.cc")
+    if not os.path.exists(src):
+        return None
+    inc = os.environ.get("PSQRT_XLA_INCLUDE")
+    if not inc:
+        try:
+            import jaxlib
+            cand = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+            inc = cand if os.path.exists(os.path.join(cand, "xla", "ffi", "api", "ffi.h")) else None
+        except Exception:
+            inc = None
+    gxx = shutil.which("g++")
+    if not gxx:
+        return None
+    if not inc:
+        r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", INCLUDE, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"xla_ffi_shim.cc does not parse against psqrt.h:\n{r.stderr}")
+        if verbose:
+            print("[psqrt build] xla_ffi_shim.cc: no XLA FFI headers here (jaxlib absent); syntax-checked only")
+        return None
+    out = os.path.join(os.path.dirname(OUT), "libpsqrt_xla.so")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    cmd = [gxx, "-std=c++17", "-O2", "-shared", "-fPIC", "-DPSQRT_HAVE_XLA_FFI", "-I", inc, "-I", INCLUDE, "-I", cuda_inc,
+           src, "-L", os.path.dirname(OUT), "-lpsqrt", "-Wl,-rpath,$ORIGIN", "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"xla shim build failed: {' '.join(cmd)}\n{r.stderr}")
+    if verbose:
+        print(f"[psqrt build] wrote {out}")
+    return out
+
+
 def build(force: bool = False, jobs: int | None = None, verbose: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
     units = []
@@ -121,6 +158,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
         raise RuntimeError(f"link failed: {r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(tag)
+    build_xla_shim(verbose)
     # drop stale objects
     keep = {os.path.basename(o) for o in objs}
     for name in os.listdir(BUILD):

@@ -482,6 +482,14 @@ int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t b
   return check_launch();
 }
 
+#if defined(PSQ_MID_TRACE)
+}  // extern "C"
+namespace psq { void mid_trace_read(unsigned long long* out); }
+extern "C" {
+// development aid (-DPSQ_MID_TRACE builds only; not declared in psqrt.h): out[2][128][16] %globaltimer stamps
+int psqrt_debug_trace(unsigned long long* out) { psq::mid_trace_read(out); return 0; }
+#endif
+
 int psqrt_fp64_probe(double* out, int iters, double* flops_out, void* stream) {
   if (!out || iters <= 0) return PSQRT_EINVAL;
   const int ctas = 148 * 4, threads = 128;

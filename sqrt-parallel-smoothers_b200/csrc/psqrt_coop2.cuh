@@ -76,6 +76,22 @@ struct PushArgs {
   int n1, n2;
 };
 
+// -DPSQ_MID_TRACE: thread 0 of every CTA of the mid scans records %globaltimer at phase boundaries (development
+// aid; read back with psqrt_debug_trace in psqrt_capi.cu).  Slot layout: [kernel kind 0/1][cta < 128][stamp < 16].
+#if defined(PSQ_MID_TRACE)
+__device__ unsigned long long g_mid_trace[2][128][16];
+__device__ __forceinline__ void mid_trace(int kind, int stamp) {
+  if (threadIdx.x == 0 && blockIdx.x < 128 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_mid_trace[kind][blockIdx.x][stamp] = t;
+  }
+}
+#define PSQ_TRACE(kind, stamp) mid_trace(kind, stamp)
+#else
+#define PSQ_TRACE(kind, stamp)
+#endif
+
 template <int N>
 __device__ __forceinline__ void ld_row(const double* __restrict__ p, double (&r)[N]) {
   if constexpr (N % 2 == 0) {
@@ -99,6 +115,19 @@ __device__ __forceinline__ void st_row(double* __restrict__ p, const double (&r)
 #pragma unroll
     for (int k = 0; k < N; ++k) p[k] = r[k];
   }
+}
+
+// Copy one dense slot (NFD doubles) with the G lanes of a group, all loads in flight before the first store
+// (a rolled load -> store loop serialises the shared-memory / DSMEM latencies).
+template <int NFD, int G>
+__device__ __forceinline__ void copy_slot(double* __restrict__ dst, const double* __restrict__ src, const int l) {
+  constexpr int PER = (NFD + G - 1) / G;
+  double v[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) v[q] = (l + q * G < NFD) ? src[l + q * G] : 0.0;
+#pragma unroll
+  for (int q = 0; q < PER; ++q)
+    if (l + q * G < NFD) dst[l + q * G] = v[q];
 }
 
 // Householder triangularisation from the right of a matrix held one ROW per lane: the lane with row index r
@@ -434,9 +463,11 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
   double* const ws = wsall + x * OP::WS;
   auto slot = [&](int s, int xx) { return slots + (s * IT + xx) * NFD; };
 
+  PSQ_TRACE(REV, 0);
   if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
   for (int k = threadIdx.x; k < (2 * IT + 1) * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
   __syncthreads();
+  PSQ_TRACE(REV, 1);
 
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
@@ -452,13 +483,26 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
       const long long gi = (REV && pass == 0) ? (Mp - 1 - sidx) : sidx;   // groups[] is in scan order already
       const bool have = x < nw;
       {
+        // all loads of the lane in flight at once (a rolled load -> store loop would serialise the L2 latencies)
+        constexpr int PER = (NF + G - 1) / G;
+        double v[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int f = l + q * G;
+          v[q] = (have && f < NF) ? __ldcg(base + f * Mp + gi) : 0.0;
+        }
         double* d = slot(0, x);
-        for (int f = l; f < NF; f += G) {
-          const int off = dmap[f];
-          d[off] = have ? __ldcg(base + f * Mp + gi) : OP::ident(off);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int f = l + q * G;
+          if (f < NF) {
+            const int off = dmap[f];
+            d[off] = have ? v[q] : OP::ident(off);
+          }
         }
       }
       __syncthreads();
+      PSQ_TRACE(REV, 2 + 6 * pass);
       int nlev = 0;
       while ((1 << nlev) < nw) ++nlev;
       int cur = 0;
@@ -474,11 +518,12 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
         double* o = slot(cur ^ 1, x);
         OP::combine(e1, e2, o, ws, l, gbase);
         if (keep) {
-          for (int k = l; k < NFD; k += G) o[k] = e2[k];
+          copy_slot<NFD, G>(o, e2, l);
         }
         __syncthreads();
         cur ^= 1;
       }
+      PSQ_TRACE(REV, 3 + 6 * pass);
       // slot(cur, x) = inclusive prefix (carry of earlier waves folded in); exclusive = the previous item's inclusive,
       // for item 0 the carry (identity in the first wave)
       if (have) {
@@ -493,7 +538,7 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
       if (x == nw - 1) {
         const double* s = slot(cur, x);
         if (w0 + IT < n_here) {                         // more waves follow
-          for (int k = l; k < NFD; k += G) carry[k] = s[k];
+          copy_slot<NFD, G>(carry, s, l);
         } else if (pass == 0) {                         // total of the group
           for (int f = l; f < NF; f += G) groups[(seq * NF + f) * Gc + blockIdx.x] = s[dmap[f]];
         } else {                                        // total of the sequence
@@ -533,13 +578,17 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
       }
       __syncthreads();
     }
+    PSQ_TRACE(REV, 4 + 6 * pass);
     if (pass == 0) {
       __threadfence();
       __syncthreads();
+      PSQ_TRACE(REV, 5);
       if (threadIdx.x == 0) s_ticket = atomicAdd(counter + seq, 1u);
       __syncthreads();
+      PSQ_TRACE(REV, 6);
       if (s_ticket != (unsigned int)(Gc - 1)) return;
       __threadfence();
+      PSQ_TRACE(REV, 7);
     }
   }
   if (ell_part && threadIdx.x < 32) {
@@ -657,7 +706,13 @@ k_carry_scan(const double* __restrict__ totals, int first, int step, int count, 
     if (x >= 1 && x <= nw) {
       const double* src = totals + ((long long)(first + step * (done + x - 1)) * B + seq) * payload;   // slot == B * payload
       double* d = slot(cur, x);
-      for (int f = l; f < NF; f += G) d[dmap[f]] = __ldcg(src + f);
+      constexpr int PER = (NF + G - 1) / G;
+      double v[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) v[q] = (l + q * G < NF) ? __ldcg(src + l + q * G) : 0.0;
+#pragma unroll
+      for (int q = 0; q < PER; ++q)
+        if (l + q * G < NF) d[dmap[l + q * G]] = v[q];
     } else if (x > nw) {
       double* d = slot(cur, x);
       for (int k = l; k < NFD; k += G) d[k] = OP::ident(k);
@@ -674,7 +729,7 @@ k_carry_scan(const double* __restrict__ totals, int first, int step, int count, 
       double* o = slot(cur ^ 1, x);
       OP::combine(e1, e2, o, ws, l, gbase);
       if (keep) {
-        for (int k = l; k < NFD; k += G) o[k] = e2[k];
+        copy_slot<NFD, G>(o, e2, l);
       }
       __syncthreads();
       cur ^= 1;
@@ -696,6 +751,199 @@ k_carry_scan(const double* __restrict__ totals, int first, int step, int count, 
       __syncthreads();
     }
   }
+}
+
+}  // namespace psq
+
+#include <cooperative_groups.h>
+
+namespace psq {
+
+// =========================================================================================
+// K2 in CLUSTER form (nx <= 4).  One combine level of k_mid_scan2 is bound by the shared-memory / shuffle
+// pipe of ONE SM once more than ~4 warps of lane groups share it (tools/bench_combine.cu: 1.6 us per level
+// with <= 2 warps, 1.7 with 4, 3.9 with the 16 warps that 64 items need) while 140 other SMs idle.  Here a group
+// of IT = CS x IC items is scanned by a thread-block CLUSTER of CS CTAs, IC items each, on CS different SMs: the
+// Kogge-Stone partner of an item may live in another CTA of the cluster and is then read through distributed
+// shared memory (copied once into a local staging slot), and the levels are separated by cluster barriers.
+// Same contract as k_mid_scan2 with Gc <= IT (one wave per pass); grid = Gc clusters.
+// =========================================================================================
+template <class OP, int NF, int CS, int IC>
+constexpr size_t mid3_smem_bytes() {
+  return sizeof(double) * (size_t)(3 * IC * OP::NFD + IC * OP::WS) + sizeof(int) * NF;
+}
+
+template <class OP, int NF, int CS, int IC, bool REV>
+__global__ void __launch_bounds__(IC * OP::G, 1)
+k_mid_scan3(double* __restrict__ items, long long M, double* __restrict__ groups, long long Gc,
+            unsigned int* __restrict__ counter, double* __restrict__ total_out, const double* __restrict__ ell_part,
+            double* __restrict__ ell_out, const PushArgs push) {
+  namespace cg = cooperative_groups;
+  constexpr int G = OP::G;
+  constexpr int NFD = OP::NFD;
+  constexpr int IT = CS * IC;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cr = (int)cluster.block_rank();            // CTA within the cluster
+  const long long grp = blockIdx.x / CS;               // cluster = group index (scan order)
+  extern __shared__ __align__(16) double mid3_sm[];
+  __shared__ unsigned int s_ticket;
+  double* const slots = mid3_sm;                       // [2][IC][NFD]
+  double* const stage = mid3_sm + 2 * IC * NFD;        // [IC][NFD] local copies of remote partners
+  double* const wsall = stage + IC * NFD;              // [IC][WS]
+  int* const dmap = reinterpret_cast<int*>(wsall + IC * OP::WS);
+  const long long seq = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int l = threadIdx.x % G;
+  const int gbase = lane - l;
+  const int x = threadIdx.x / G;                       // item within the CTA
+  const int X = cr * IC + x;                           // item within the cluster
+  double* const ws = wsall + x * OP::WS;
+  auto slot = [&](int s, int xx) { return slots + (s * IC + xx) * NFD; };
+
+  PSQ_TRACE(REV, 0);
+  if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
+  for (int k = threadIdx.x; k < 3 * IC * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
+  __syncthreads();
+  PSQ_TRACE(REV, 1);
+
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    double* const arr = pass ? groups : items;
+    const long long Mp = pass ? Gc : M;
+    double* const base = arr + seq * NF * Mp;
+    const long long first = pass ? 0 : grp * IT;
+    const int nw = (int)((Mp - first < IT) ? Mp - first : IT);     // items this cluster scans in this pass
+    const long long sidx = first + X;
+    const long long gi = (REV && pass == 0) ? (Mp - 1 - sidx) : sidx;
+    const bool have = X < nw;
+    {
+      constexpr int PER = (NF + G - 1) / G;
+      double v[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int f = l + q * G;
+        v[q] = (have && f < NF) ? __ldcg(base + f * Mp + gi) : 0.0;
+      }
+      double* d = slot(0, x);
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int f = l + q * G;
+        if (f < NF) {
+          const int off = dmap[f];
+          d[off] = have ? v[q] : OP::ident(off);
+        }
+      }
+    }
+    cluster.sync();
+    PSQ_TRACE(REV, 2 + 6 * pass);
+    int nlev = 0;
+    while ((1 << nlev) < nw) ++nlev;
+    int cur = 0;
+#pragma unroll 1
+    for (int lev = 0; lev < nlev; ++lev) {
+      const int d = 1 << lev;
+      const bool keep = X < d;                          // combines with itself, result discarded
+      const int Xp = keep ? X : X - d;
+      const int rp = Xp / IC, xp = Xp % IC;
+      const double* e1 = slot(cur, xp);
+      if (rp != cr) {                                   // partner in another CTA of the cluster: DSMEM -> staging slot
+        const double* r = cluster.map_shared_rank(slot(cur, xp), rp);
+        double* st = stage + x * NFD;
+        copy_slot<NFD, G>(st, r, l);
+        e1 = st;
+      }
+      __syncwarp();
+      const double* e2 = slot(cur, x);
+      double* o = slot(cur ^ 1, x);
+      OP::combine(e1, e2, o, ws, l, gbase);
+      if (keep) {
+        copy_slot<NFD, G>(o, e2, l);
+      }
+      cluster.sync();
+      cur ^= 1;
+    }
+    PSQ_TRACE(REV, 3 + 6 * pass);
+    // slot(cur, .) = inclusive prefixes; exclusive = the previous item's (identity for item 0), possibly remote
+    if (have) {
+      const int Xq = (X > 0) ? X - 1 : 0;
+      const double* s = (Xq / IC == cr) ? slot(cur, Xq % IC) : cluster.map_shared_rank(slot(cur, Xq % IC), Xq / IC);
+      constexpr int PER = (NF + G - 1) / G;
+      double v[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int f = l + q * G;
+        if (f < NF) v[q] = (X == 0) ? OP::ident(dmap[f]) : s[dmap[f]];
+      }
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int f = l + q * G;
+        if (f < NF) base[f * Mp + gi] = v[q];
+      }
+    }
+    if (X == nw - 1) {
+      const double* s = slot(cur, x);
+      if (pass == 0) {                                  // total of the group
+        for (int f = l; f < NF; f += G) groups[(seq * NF + f) * Gc + grp] = s[dmap[f]];
+      } else {                                          // total of the sequence
+        if (total_out)
+          for (int f = l; f < NF; f += G) total_out[seq * NF + f] = s[dmap[f]];
+        if (push.on) {
+          const PeerCtx& pc = push.pc;
+          const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+          unsigned long long epoch = 0;
+          if (l == 0) {
+            volatile unsigned long long* c =
+                reinterpret_cast<volatile unsigned long long*>(pc.bufs[pc.rank] + pc.ctr_off + seq);
+            epoch = *c + 1ull;
+            *c = epoch;
+          }
+          epoch = __shfl_sync(gmask, epoch, gbase);
+          const long long off = pc.data_off + (long long)(epoch & 1ull) * pc.n_ranks * pc.slot +
+                                (long long)pc.rank * pc.slot + seq * pc.payload;
+          for (int r = 0; r < pc.n_ranks; ++r) {
+            double* dst = pc.bufs[r] + off;
+            for (int f = l; f < NF; f += G) dst[f] = s[dmap[f]];
+            for (int k = l; k < push.n1; k += G) dst[NF + k] = push.x1[seq * push.s1 + k];
+            for (int k = l; k < push.n2; k += G) dst[NF + push.n1 + k] = push.x2[seq * push.s2 + k];
+          }
+          __threadfence_system();
+          __syncwarp(gmask);
+          if (l == 0) {
+            for (int r = 0; r < pc.n_ranks; ++r) {
+              volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
+                  pc.bufs[r] + pc.flags_off + (long long)pc.rank * pc.batch + seq);
+              *f = epoch;
+            }
+          }
+        }
+      }
+    }
+    PSQ_TRACE(REV, 4 + 6 * pass);
+    if (pass == 0) {
+      // the cluster that takes the last ticket goes on to scan the group totals
+      __threadfence();
+      cluster.sync();                                   // all remote reads of this pass are done, all stores fenced
+      PSQ_TRACE(REV, 5);
+      if (cr == 0 && threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(counter + seq, 1u);
+        for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(&s_ticket, r) = t;
+      }
+      cluster.sync();
+      PSQ_TRACE(REV, 6);
+      if (s_ticket != (unsigned int)(Gc - 1)) return;
+      __threadfence();
+      PSQ_TRACE(REV, 7);
+    }
+  }
+  if (ell_part && cr == 0 && threadIdx.x < 32) {
+    double sum = 0.0;
+    for (long long i2 = lane; i2 < M; i2 += 32) sum += ell_part[seq * M + i2];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if (lane == 0) ell_out[seq] = sum;
+  }
+  if (cr == 0 && threadIdx.x == 0) counter[seq] = 0u;
+  cluster.sync();                                       // nobody leaves while its shared memory may still be read
 }
 
 }  // namespace psq

@@ -178,12 +178,60 @@ void launch_mid2(double* items, long long M, long long B, double* groups, unsign
   kern<<<dim3((unsigned)Gc, (unsigned)B, 1), IT * OP::G, smem, st>>>(items, M, groups, Gc, counter, total, ell_part,
                                                                      ell_out, pa);
 }
+// Cluster form (psqrt_coop2.cuh, k_mid_scan3): the IT = 64 items of a group spread over a cluster of CS CTAs on CS SMs.
+// PSQRT_MID_CLUSTER: bit 0 = filtering scan, bit 1 = smoothing scan (default below; 0 = single-CTA groups everywhere).
+constexpr bool kClusterMid = (PSQ_N <= 4);
+constexpr int kClusterDefault = 1;
+inline int cluster_mask() {
+  static const int m = [] {
+    const char* e = getenv("PSQRT_MID_CLUSTER");
+    return e ? atoi(e) : kClusterDefault;
+  }();
+  return m;
+}
+template <class OP, int NF, bool REV>
+bool launch_mid3(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
+                 const double* ell_part, double* ell_out, const PushArgs* push, cudaStream_t st) {
+  if constexpr (kClusterMid) {
+    constexpr int IT = MidCfg<N>::IT, CS = 4, IC = IT / CS;
+    const long long Gc = (M + IT - 1) / IT;
+    if (Gc > IT) return false;                     // more than one wave at the top level: single-CTA kernel
+    // one CTA per SM: the dynamic shared-memory request is padded beyond half an SM
+    constexpr size_t need = mid3_smem_bytes<OP, NF, CS, IC>();
+    constexpr size_t smem = need > 116 * 1024 ? need : 116 * 1024;
+    auto kern = k_mid_scan3<OP, NF, CS, IC, REV>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    PushArgs pa;
+    if (push) pa = *push; else memset(&pa, 0, sizeof(pa));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(Gc * CS), (unsigned)B, 1);
+    cfg.blockDim = dim3(IC * OP::G, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, items, M, groups, Gc, counter, total, ell_part, ell_out, pa) == cudaSuccess;
+  }
+  return false;
+}
 void mid_filter(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 const PushArgs* push, cudaStream_t st) {
+  if ((cluster_mask() & 1) &&
+      launch_mid3<CoopF2<N>, FElem<N>::NF, false>(items, M, B, groups, counter, total, nullptr, nullptr, push, st))
+    return;
   launch_mid2<CoopF2<N>, FElem<N>::NF, false>(items, M, B, groups, counter, total, nullptr, nullptr, push, st);
 }
 void mid_smooth(double* items, long long M, long long B, double* groups, unsigned int* counter, double* total,
                 const double* ell_part, double* ell_out, const PushArgs* push, cudaStream_t st) {
+  if ((cluster_mask() & 2) &&
+      launch_mid3<CoopS2<N>, SElem<N>::NF, true>(items, M, B, groups, counter, total, ell_part, ell_out, push, st))
+    return;
   launch_mid2<CoopS2<N>, SElem<N>::NF, true>(items, M, B, groups, counter, total, ell_part, ell_out, push, st);
 }
 // Time-shard carries: log-depth scan of the shard totals after a seed element built from the prior / terminal state.
@@ -348,6 +396,13 @@ const LaunchN kTable = {N,
 }  // namespace
 
 const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return &kTable; }
+
+#if defined(PSQ_MID_TRACE) && PSQ_N == 4
+void mid_trace_read(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_mid_trace, sizeof(g_mid_trace));
+}
+#endif
 
 
 }  // namespace psq

@@ -31,6 +31,13 @@ class _Ssm(ctypes.Structure):
                [(n, ctypes.c_void_p) for n in ("hF", "hcholQ", "hb", "hH", "hcholR", "hc")]
 
 
+class Peer(ctypes.Structure):
+    """psqrt_peer (include/psqrt.h): one phase of the time-shard exchange over peer-mapped memory."""
+    _fields_ = [("bufs", ctypes.c_void_p), ("rank", ctypes.c_int32), ("n_ranks", ctypes.c_int32),
+                ("batch", ctypes.c_int64), ("flags_off", ctypes.c_int64), ("ctr_off", ctypes.c_int64),
+                ("data_off", ctypes.c_int64), ("slot", ctypes.c_int64), ("payload", ctypes.c_int64)]
+
+
 class Plan(ctypes.Structure):
     _fields_ = [("chunk_len", ctypes.c_int32), ("n_chunks", ctypes.c_int64), ("n_chunks_pad", ctypes.c_int64),
                 ("n_warps", ctypes.c_int64), ("nf_filter", ctypes.c_int32), ("nf_smoother", ctypes.c_int32)]
@@ -42,7 +49,7 @@ EXPORTS = (
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
-    "psqrt_fp64_probe", "psqrt_peer_push", "psqrt_peer_wait", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
+    "psqrt_fp64_probe", "psqrt_peer_layout", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -70,6 +77,9 @@ def load() -> ctypes.CDLL:
                                           ctypes.c_int]
     lib.psqrt_get_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                    ctypes.POINTER(Plan)]
+    lib.psqrt_peer_layout.restype = ctypes.c_int64
+    lib.psqrt_peer_layout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(Peer),
+                                      ctypes.POINTER(Peer)]
     _lib = lib
     return lib
 
@@ -284,7 +294,20 @@ def smoother(ssm: LinearizedSSM, fm: torch.Tensor, fL: torch.Tensor, *, chunk_le
 
 
 # ---- staged calls (time-sharded runs; see psqrt/dist.py) ---------------------------------------
-def filter_reduce(ssm, y, nx, chunk_len=0):
+def _peer_arg(peer):
+    return ctypes.byref(peer) if peer is not None else None
+
+
+def peer_layout(nx: int, n_ranks: int, batch: int):
+    """-> (words per exchange buffer, filter-phase Peer, smoother-phase Peer) with the offsets filled in."""
+    f, s = Peer(), Peer()
+    n = int(load().psqrt_peer_layout(int(nx), int(n_ranks), ctypes.c_int64(batch), ctypes.byref(f), ctypes.byref(s)))
+    if n <= 0:
+        raise PsqrtError(f"psqrt_peer_layout: unsupported nx={nx}")
+    return n, f, s
+
+
+def filter_reduce(ssm, y, nx, chunk_len=0, peer=None):
     lib = load()
     B, T, ny = y.shape
     _require(nx, ny)
@@ -296,23 +319,23 @@ def filter_reduce(ssm, y, nx, chunk_len=0):
     with torch.cuda.device(y.device):
         rc = lib.psqrt_filter_reduce(ctypes.byref(s), _ptr(y), nx, ny, ctypes.c_int64(T), ctypes.c_int64(B), chunk_len,
                                      _ptr(total), ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()),
-                                     _stream())
+                                     _peer_arg(peer), _stream())
     _check(rc, "psqrt_filter_reduce")
     return total
 
 
-def carry_filter(totals, rank, m0, L0):
+def carry_filter(totals, rank, m0, L0, peer=None):
     lib = load()
     B, nx = m0.shape
     cm, cL = torch.empty_like(m0), torch.empty_like(L0)
     with torch.cuda.device(m0.device):
         rc = lib.psqrt_carry_filter(_ptr(totals), rank, ctypes.c_int64(B), nx, _ptr(m0), _ptr(L0), _ptr(cm), _ptr(cL),
-                                    _stream())
+                                    _peer_arg(peer), _stream())
     _check(rc, "psqrt_carry_filter")
     return cm, cL
 
 
-def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_len=0):
+def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_len=0, peer=None):
     lib = load()
     B, T, ny = y.shape
     nx = carry_m.shape[-1]
@@ -328,19 +351,21 @@ def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_l
     with torch.cuda.device(dev):
         rc = lib.psqrt_filter_apply(ctypes.byref(s), _ptr(y), _ptr(carry_m), _ptr(carry_L), nx, ny, ctypes.c_int64(T),
                                     ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(ell), _ptr(stotal),
-                                    ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), _stream())
+                                    ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), _peer_arg(peer),
+                                    _stream())
     _check(rc, "psqrt_filter_apply")
     fm._psqrt_stage = _stage_token(dev)    # smoother_apply reads the packed states this call left in the workspace
     return fm, fL, ell, stotal
 
 
-def carry_smoother(totals, rank, n_ranks, mT, LT):
+def carry_smoother(totals, rank, n_ranks, mT, LT, peer=None):
+    """With `peer`, totals / mT / LT are only templates for the output shapes (the kernel reads the exchange buffer)."""
     lib = load()
     B, nx = mT.shape
     cm, cL = torch.empty_like(mT), torch.empty_like(LT)
     with torch.cuda.device(mT.device):
         rc = lib.psqrt_carry_smoother(_ptr(totals), rank, n_ranks, ctypes.c_int64(B), nx, _ptr(mT), _ptr(LT), _ptr(cm),
-                                      _ptr(cL), _stream())
+                                      _ptr(cL), _peer_arg(peer), _stream())
     _check(rc, "psqrt_carry_smoother")
     return cm, cL
 
@@ -366,28 +391,6 @@ def smoother_apply(ssm, fm, fL, carry_m, carry_L, *, write_terminal=True, chunk_
                                       ctypes.c_size_t(ws.numel()), _stream())
     _check(rc, "psqrt_smoother_apply")
     return sm, sL
-
-
-def peer_push(segments, peer_bufs: torch.Tensor, peer_flags: torch.Tensor, rank: int, n_ranks: int, epoch_ctr_ptr: int):
-    """psqrt_peer_push: segments = up to three (src tensor, destination offset in doubles); peer_bufs / peer_flags are
-    int64 DEVICE tensors holding the n_ranks peer base pointers; epoch_ctr_ptr: device address of the epoch word."""
-    lib = load()
-    segs = list(segments) + [(None, 0)] * (3 - len(segments))
-    args = []
-    for src, off in segs:
-        args += [_ptr(src), ctypes.c_int64(0 if src is None else src.numel()), ctypes.c_int64(off)]
-    with torch.cuda.device(peer_bufs.device):
-        rc = lib.psqrt_peer_push(*args, ctypes.c_void_p(peer_bufs.data_ptr()), ctypes.c_void_p(peer_flags.data_ptr()),
-                                 int(rank), int(n_ranks), ctypes.c_void_p(epoch_ctr_ptr), _stream())
-    _check(rc, "psqrt_peer_push")
-
-
-def peer_wait(flags_ptr: int, first: int, last: int, epoch_ctr_ptr: int, device):
-    lib = load()
-    with torch.cuda.device(device):
-        rc = lib.psqrt_peer_wait(ctypes.c_void_p(flags_ptr), int(first), int(last), ctypes.c_void_p(epoch_ctr_ptr),
-                                 _stream())
-    _check(rc, "psqrt_peer_wait")
 
 
 # ---- element-level seams ------------------------------------------------------------------------

@@ -53,70 +53,37 @@ def _all_gather(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
 
 
 class PeerExchange:
-    """The two exchanges of a time-sharded pass over peer-mapped memory instead of NCCL.
+    """The two exchanges of a time-sharded pass over peer-mapped memory instead of NCCL, FUSED into the kernels that
+    produce and consume the shard totals (include/psqrt.h, "staged calls"; csrc/psqrt_coop2.cuh).
 
     Every rank owns one exchange buffer (torch symmetric memory: CUDA IPC / fabric handles, mapped into every
-    peer of the node).  A rank stores its shard total straight into slot `rank` of EVERY peer's buffer over
-    NVLink and raises that peer's flag (psqrt_peer_push); the consumer spins on its local flags in stream order
-    (psqrt_peer_wait) and the carry kernels read the totals from local memory.  No collective call, no host
-    synchronisation, no per-pass host argument (flags are monotonic epochs counted on the device), so a whole
-    pass can be captured in a CUDA graph.
+    peer of the node).  The CTA that finishes the mid-level scan of a rank stores the shard total straight into slot
+    `rank` of EVERY rank's buffer over NVLink and publishes the pass number there; the consumer's carry kernel waits
+    for the pass number of ALL ranks, then folds the totals it needs (log-depth) out of local memory.  No
+    collective call, no separate push / wait launches, no host synchronisation, no per-pass host argument (pass
+    numbers are counted on the device), so a whole pass is captured in one CUDA graph.
 
-    A slot is rewritten only after its readers are done: rank a can push the totals of pass p + 1 only after its
-    own pass p finished, i.e. after it consumed what every reader b of that slot pushed LATER in pass p than b's
-    read of the slot (filter totals are read before the smoother push, smoother totals before the next pass's
-    filter push).
+    Slots are double-buffered by pass parity, and since every carry waits for all ranks no rank can be more than one
+    pass ahead of a reader of its slot -- with or without the smoother phase."""
 
-    Layout (doubles): [2][R] flag words (filter, smoother) | 2 epoch words | F [R][B nf_f] | S [R][B nf_s] |
-    M [R][B nx] | L [R][B nx^2]."""
-
-    def __init__(self, world, rank, B, nf_f, nf_s, nx, device, group=None):
+    def __init__(self, world, rank, B, nx, device, group=None, ops=None):
+        import ctypes
         import torch.distributed._symmetric_memory as symm_mem
-        R = world
-        self.R, self.rank, self.B, self.nx, self.nf_f, self.nf_s = R, rank, B, nx, nf_f, nf_s
-        self.sizes = (B * nf_f, B * nf_s, B * nx, B * nx * nx)
-        self.head = 2 * R + 2
-        n = self.head + R * sum(self.sizes)
+        if ops is None:
+            from . import _lib as ops
+        self.R, self.rank, self.B, self.nx = world, rank, B, nx
+        n_words, self.filter_phase, self.smoother_phase = ops.peer_layout(nx, world, B)
         grp = group if group is not None else dist.group.WORLD
-        self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+        self.buf = symm_mem.empty(n_words, dtype=torch.float64, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, grp)
-        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.peer_flags = [torch.tensor([p + 8 * R * ph for p in ptrs], dtype=torch.int64, device=device) for ph in (0, 1)]
-        self.flags_ptr = [self.buf.data_ptr() + 8 * R * ph for ph in (0, 1)]
-        self.epoch_ptr = [self.buf.data_ptr() + 8 * (2 * R + ph) for ph in (0, 1)]
+        self.peer_bufs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        for ph in (self.filter_phase, self.smoother_phase):
+            ph.bufs = ctypes.c_void_p(self.peer_bufs.data_ptr())
+            ph.rank = rank
         self.device = device
         torch.cuda.synchronize(device)
-        dist.barrier(group)          # every buffer is zeroed before anyone pushes
-
-    def _region(self, which):
-        """(offset of the region in doubles, slot size)"""
-        return self.head + self.R * sum(self.sizes[:which]), self.sizes[which]
-
-    def _view(self, which, shape):
-        off, slot = self._region(which)
-        return self.buf[off:off + self.R * slot].view((self.R,) + shape)
-
-    def exchange_filter(self, ops, ftotal):
-        """-> totals [R, B, nf_f]; entries of ranks < rank are valid when the returned view is read in stream order."""
-        off, slot = self._region(0)
-        ops.peer_push([(ftotal.contiguous(), off + self.rank * slot)], self.peer_bufs, self.peer_flags[0], self.rank,
-                      self.R, self.epoch_ptr[0])
-        ops.peer_wait(self.flags_ptr[0], 0, self.rank - 1, self.epoch_ptr[0], self.device)
-        return self._view(0, (self.B, self.nf_f))
-
-    def exchange_smoother(self, ops, stotal, m_last, L_last):
-        """-> (stotals [R, B, nf_s], mT [B, nx], LT [B, nx, nx] of the last rank)."""
-        R, r = self.R, self.rank
-        segs = []
-        for which, t in ((1, stotal), (2, m_last), (3, L_last)):
-            off, slot = self._region(which)
-            segs.append((t.contiguous(), off + r * slot))
-        ops.peer_push(segs, self.peer_bufs, self.peer_flags[1], r, R, self.epoch_ptr[1])
-        ops.peer_wait(self.flags_ptr[1], r + 1, R - 1, self.epoch_ptr[1], self.device)
-        return (self._view(1, (self.B, self.nf_s)), self._view(2, (self.B, self.nx))[R - 1],
-                self._view(3, (self.B, self.nx, self.nx))[R - 1])
+        dist.barrier(group)          # every buffer is zeroed before anyone publishes
 
 
 class TimeShardedSmoother:
@@ -136,11 +103,11 @@ class TimeShardedSmoother:
         self._peer = None
         self.exchange_error = None
 
-    def _peer_exchange(self, B, nf_f, nf_s):
+    def _peer_exchange(self, B):
         if self._peer is None or self._peer.B != B:
             err = None
             try:
-                peer = PeerExchange(self.world, self.rank, B, nf_f, nf_s, self.nx, self.device, self.group)
+                peer = PeerExchange(self.world, self.rank, B, self.nx, self.device, self.group, ops=self.ops)
             except Exception as e:            # no symmetric memory on this system
                 peer, err = None, repr(e)
             # the ranks must agree: if the rendezvous failed anywhere, everybody uses the NCCL all-gathers
@@ -163,34 +130,32 @@ class TimeShardedSmoother:
         log-likelihood of the WHOLE sequence (same value on every rank) or None."""
         ops, R, r = self.ops, self.world, self.rank
         B = y.shape[0]
-        ftotal = ops.filter_reduce(ssm, y, self.nx, chunk_len=self.chunk_len)                 # [B, nf_filter]
-        peer = None
-        # Slot reuse of the single-buffered peer exchange is ordered by the smoother exchange of the same pass
-        # (see PeerExchange); a filter-only pass has no such back-edge, so it takes the all-gather
-        if self.exchange == "peer" and smooth:
-            nf_s = (3 * self.nx * self.nx + 3 * self.nx) // 2
-            peer = self._peer_exchange(B, ftotal.shape[-1], nf_s)
+        peer = self._peer_exchange(B) if self.exchange == "peer" else None
+        m0, L0 = m0.contiguous(), L0.contiguous()
         if peer is not None:
-            totals = peer.exchange_filter(ops, ftotal)
+            # exchange fused into the kernels: K2's last CTA publishes the total, the carry kernel waits + folds
+            ops.filter_reduce(ssm, y, self.nx, chunk_len=self.chunk_len, peer=peer.filter_phase)
+            cm, cL = ops.carry_filter(None, r, m0, L0, peer=peer.filter_phase)
         else:
+            ftotal = ops.filter_reduce(ssm, y, self.nx, chunk_len=self.chunk_len)             # [B, nf_filter]
             totals = _all_gather(ftotal, R, self.group)                                      # [R, B, nf]
-        cm, cL = ops.carry_filter(totals, r, m0.contiguous(), L0.contiguous())
-        fm, fL, ell, stotal = ops.filter_apply(ssm, y, cm, cL, smooth=smooth, loglik=loglik,
-                                               chunk_len=self.chunk_len)
+            cm, cL = ops.carry_filter(totals, r, m0, L0)
+        fm, fL, ell, stotal = ops.filter_apply(ssm, y, cm, cL, smooth=smooth, loglik=loglik, chunk_len=self.chunk_len,
+                                               **({"peer": peer.smoother_phase} if (peer is not None and smooth) else {}))
         if loglik and R > 1:
             dist.all_reduce(ell, op=dist.ReduceOp.SUM, group=self.group)
         if not smooth:
             return fm, fL, None, None, ell
         nfs = stotal.shape[-1]
         if peer is not None:
-            stotals, mT, LT = peer.exchange_smoother(ops, stotal, fm[:, -1], fL[:, -1])
+            sm_c, sL_c = ops.carry_smoother(None, r, R, m0, L0, peer=peer.smoother_phase)   # m0 / L0: shape templates
         else:
             payload = torch.cat([stotal, fm[:, -1], fL[:, -1].reshape(B, -1)], dim=-1)       # [B, nfs + nx + nx^2]
             gathered = _all_gather(payload, R, self.group)
             stotals = gathered[:, :, :nfs].contiguous()
             mT = gathered[R - 1, :, nfs:nfs + self.nx].contiguous()
             LT = gathered[R - 1, :, nfs + self.nx:].reshape(B, self.nx, self.nx).contiguous()
-        sm_c, sL_c = ops.carry_smoother(stotals, r, R, mT, LT)
+            sm_c, sL_c = ops.carry_smoother(stotals, r, R, mT, LT)
         sm, sL = ops.smoother_apply(ssm, fm, fL, sm_c, sL_c, write_terminal=True, chunk_len=self.chunk_len)
         return fm, fL, sm, sL, ell
 

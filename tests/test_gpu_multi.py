@@ -1,5 +1,5 @@
 """Time-sharded pass on >= 2 real GPUs (one process per GPU, torchrun): both exchange modes -- NCCL all-gathers and
-P2P stores into peer-mapped buffers (psqrt_peer_push / psqrt_peer_wait) -- against the single-GPU pass on the same
+P2P stores into peer-mapped buffers fused into the mid-scan / carry kernels (psqrt_peer) -- against the single-GPU pass on the same
 sequence.  Skipped on boxes with fewer than two GPUs; the host logic of the sharding is covered on the CPU by
 tests/test_dist_gloo.py."""
 import os
