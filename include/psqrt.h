@@ -221,6 +221,40 @@ int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id
                             const double* nom_L, int64_t count, const double* m_q, const double* chol_q,
                             double* F, double* chol, double* b, void* stream);
 
+/* ---- forward-mode tangent (JVP) of the pass and of its log-likelihood: the gradient path ---------------------
+ * Replaces jax.jvp / jax.value_and_grad through parsmooth.methods.filter_smoother / filtering(..., return_loglikelihood=True)
+ * (methods.py:14-47, 72-75; parallel/_filtering.py:13-61,149-154; parallel/_smoothing.py:14-57) and, iterated, the
+ * implicit differentiation of the fixed point (parsmooth/_utils.py:103-146).  One tangent direction, one sequence.
+ *
+ * psqrt_ssm_tangent: the directional derivative of the linearised model, COVARIANCE form for the noises:
+ *   dF [nx,nx], dQ [nx,nx] = d(cholQ cholQ^T) (symmetric), db [nx], dH [ny,nx], dR [ny,ny] = d(cholR cholR^T), dc [ny];
+ *   *_ts = stride in doubles between time steps (0 = the same for every step); a NULL pointer is a zero tangent.
+ * psqrt_filter_smoother_tangent: given the primal trajectories of psqrt_filter_smoother on the same inputs
+ *   (fm, fL filtered with index 0 = the prior; sm, sL smoothed, NULL = filter only) and the tangent of the prior
+ *   (dm0 [nx], dP0 [nx,nx] = d(L0 L0^T); NULL = 0), writes the tangents of the filtered moments dfm [T+1,nx],
+ *   dfP [T+1,nx,nx] (= d(fL fL^T)), of the smoothed moments dsm, dsP (both NULL = skip) and of the log-likelihood
+ *   dell [1] (NULL = skip).  The tangent recursions are affine maps (Phi, w, c, C) composed by an associative scan of
+ *   matrix products (csrc/psqrt_tangent.cu); nothing is triangularised.
+ * psqrt_cov_tangent_to_chol: dL [count,n,n] with d(L L^T) = dP for LOWER-triangular nonsingular L (what the pass writes).
+ * psqrt_linearize_builtin_tangent: tangent of psqrt_linearize_builtin along (dnom_m, dnom_L [lower], dmodel_params,
+ *   dm_q, dQ_q = d(chol_q chol_q^T)); any of them may be NULL (= 0).  Outputs dF [count,d,n], db [count,d] and dQ
+ *   [count,d,d] (covariance form; for PSQRT_LIN_EXTENDED with a functional model dQ is not written -- it is dQ_q). */
+typedef struct psqrt_ssm_tangent {
+  const double *dF, *dQ, *db, *dH, *dR, *dc;
+  int64_t dF_ts, dQ_ts, db_ts, dH_ts, dR_ts, dc_ts;
+} psqrt_ssm_tangent;
+size_t psqrt_tangent_workspace_bytes(int nx, int ny, int64_t T);
+int psqrt_filter_smoother_tangent(const psqrt_ssm* ssm, const psqrt_ssm_tangent* dssm, const double* y, int nx, int ny,
+                                  int64_t T, const double* fm, const double* fL, const double* sm, const double* sL,
+                                  const double* dm0, const double* dP0, double* dfm, double* dfP, double* dsm,
+                                  double* dsP, double* dell, void* ws, size_t ws_bytes, void* stream);
+int psqrt_cov_tangent_to_chol(const double* L, const double* dP, double* dL, int n, int64_t count, void* stream);
+int psqrt_linearize_builtin_tangent(int model_id, const double* model_params, const double* dmodel_params, int lin_id,
+                                    const double* xi, const double* wm, const double* wc, int n_points,
+                                    const double* nom_m, const double* nom_L, const double* dnom_m,
+                                    const double* dnom_L, int64_t count, const double* dm_q, const double* dQ_q,
+                                    double* dF, double* dQ, double* db, void* stream);
+
 /* ---- measurement aid (bench.py): FP64 FMA throughput probe ------------------------------------
  * Launches 148 x 4 CTAs of 128 threads, each thread running 8 independent chains of `iters` x 16 dependent
  * DFMAs, and writes the flop count of the launch to *flops_out (host).  The caller times the launch with

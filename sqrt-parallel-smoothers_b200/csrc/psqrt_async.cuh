@@ -14,6 +14,17 @@
 
 namespace psq {
 
+// Programmatic dependent launch (sm_90+): the kernels of a pass are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs may be scheduled while its predecessor
+// in the stream is still draining.  Every kernel calls pdl_entry() before it touches global memory:
+// griddepcontrol.wait blocks until the predecessor grid has completed and flushed (a no-op for a plain launch);
+// launch_dependents lets the successor's launch overlap this kernel (it waits in its own pdl_entry()).  Because every
+// kernel of the chain waits, completion is transitive: kernel i+2 never runs ahead of kernel i.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");

@@ -466,6 +466,7 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
   PSQ_TRACE(REV, 0);
   if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
   for (int k = threadIdx.x; k < (2 * IT + 1) * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
+  pdl_entry();                                         // shared-memory set-up overlaps the predecessor's tail
   __syncthreads();
   PSQ_TRACE(REV, 1);
 
@@ -803,6 +804,7 @@ k_mid_scan3(double* __restrict__ items, long long M, double* __restrict__ groups
   PSQ_TRACE(REV, 0);
   if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
   for (int k = threadIdx.x; k < 3 * IC * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
+  pdl_entry();                                         // shared-memory set-up overlaps the predecessor's tail
   __syncthreads();
   PSQ_TRACE(REV, 1);
 

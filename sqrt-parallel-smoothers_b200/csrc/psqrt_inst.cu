@@ -68,10 +68,48 @@ template <int NN>
 bool vec2_ok(const void* m, const void* L) {
   return NN % 2 == 0 && aligned16(m) && aligned16(L);
 }
+// PSQRT_PDL=1 turns programmatic dependent launch on (psqrt_async.cuh, pdl_entry).  Default off: measured on B200 the
+// early-scheduled successor CTAs slow the sweeps' tails more than the hidden launch latency gains (T = 1e6, nx = 4:
+// 0.283 ms per pass with it, 0.276 ms without; profiles/r02_pdl_ab.txt).
+inline bool pdl_on() {
+  static const bool on = [] {
+    const char* e = getenv("PSQRT_PDL");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
+// Launch of a kernel that calls pdl_entry(): optional cluster dimension, programmatic stream serialization.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_on()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 template <class KERN, class... Args>
 void launch_sweep(KERN kern, size_t smem, long long Ppad, long long B, cudaStream_t st, Args... args) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<sweep_grid(Ppad, B), kBlock, smem, st>>>(args...);
+  launch_pdl(kern, sweep_grid(Ppad, B), dim3(kBlock, 1, 1), smem, st, 1, args...);
 }
 
 template <int NY>
@@ -175,8 +213,8 @@ void launch_mid2(double* items, long long M, long long B, double* groups, unsign
   const long long Gc = (M + IT - 1) / IT;
   PushArgs pa;
   if (push) pa = *push; else memset(&pa, 0, sizeof(pa));
-  kern<<<dim3((unsigned)Gc, (unsigned)B, 1), IT * OP::G, smem, st>>>(items, M, groups, Gc, counter, total, ell_part,
-                                                                     ell_out, pa);
+  launch_pdl(kern, dim3((unsigned)Gc, (unsigned)B, 1), dim3(IT * OP::G, 1, 1), smem, st, 1, items, M, groups, Gc,
+             counter, total, ell_part, ell_out, pa);
 }
 // Cluster form (psqrt_coop2.cuh, k_mid_scan3): the IT = 64 items of a group spread over a cluster of CS CTAs on CS SMs.
 // PSQRT_MID_CLUSTER: bit 0 = filtering scan, bit 1 = smoothing scan (default below; 0 = single-CTA groups everywhere).
@@ -203,20 +241,8 @@ bool launch_mid3(double* items, long long M, long long B, double* groups, unsign
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     PushArgs pa;
     if (push) pa = *push; else memset(&pa, 0, sizeof(pa));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(Gc * CS), (unsigned)B, 1);
-    cfg.blockDim = dim3(IC * OP::G, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CS;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, items, M, groups, Gc, counter, total, ell_part, ell_out, pa) == cudaSuccess;
+    return launch_pdl(kern, dim3((unsigned)(Gc * CS), (unsigned)B, 1), dim3(IC * OP::G, 1, 1), smem, st, CS, items, M,
+                      groups, Gc, counter, total, ell_part, ell_out, pa) == cudaSuccess;
   }
   return false;
 }

@@ -302,6 +302,7 @@ k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long P
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
+  pdl_entry();
   if (c == 0) counter[seq] = 0u;  // arms the ticket of the mid-level scan that follows
   FAcc<N> acc;
   acc.set_identity();
@@ -531,6 +532,7 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
 
+  pdl_entry();
   if (SMOOTH && c == 0) counter[seq] = 0u;
   LaneRing<NY, kYDepth> yring(smem_raw + OUT::smem_bytes(kBlock));
 #pragma unroll
@@ -661,6 +663,7 @@ k_smooth_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   const long long Mw = Ppad / 32;
   const long long k0 = c * K;
   const long long k1 = (k0 + K < T) ? k0 + K : T;
+  pdl_entry();
   if ((c - lane) * K >= T) return;  // the whole warp lies past the end of the sequence
   const int len = (k1 > k0) ? (int)(k1 - k0) : 0;
   double* smS = sm + seq * (T + 1) * N;

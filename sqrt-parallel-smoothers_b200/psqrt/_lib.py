@@ -38,6 +38,12 @@ class Peer(ctypes.Structure):
                 ("data_off", ctypes.c_int64), ("slot", ctypes.c_int64), ("payload", ctypes.c_int64)]
 
 
+class _SsmTangent(ctypes.Structure):
+    """psqrt_ssm_tangent (include/psqrt.h): one tangent direction of the linearised model, covariance form."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("dF", "dQ", "db", "dH", "dR", "dc")] + \
+               [(n + "_ts", ctypes.c_int64) for n in ("dF", "dQ", "db", "dH", "dR", "dc")]
+
+
 class Plan(ctypes.Structure):
     _fields_ = [("chunk_len", ctypes.c_int32), ("n_chunks", ctypes.c_int64), ("n_chunks_pad", ctypes.c_int64),
                 ("n_warps", ctypes.c_int64), ("nf_filter", ctypes.c_int32), ("nf_smoother", ctypes.c_int32)]
@@ -50,6 +56,8 @@ EXPORTS = (
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
     "psqrt_fp64_probe", "psqrt_peer_layout", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
+    "psqrt_tangent_workspace_bytes", "psqrt_filter_smoother_tangent", "psqrt_cov_tangent_to_chol",
+    "psqrt_linearize_builtin_tangent",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -77,6 +85,8 @@ def load() -> ctypes.CDLL:
                                           ctypes.c_int]
     lib.psqrt_get_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                    ctypes.POINTER(Plan)]
+    lib.psqrt_tangent_workspace_bytes.restype = ctypes.c_size_t
+    lib.psqrt_tangent_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
     lib.psqrt_peer_layout.restype = ctypes.c_int64
     lib.psqrt_peer_layout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(Peer),
                                       ctypes.POINTER(Peer)]
@@ -626,3 +636,96 @@ def linearize_builtin(model_id: int, params, lin_id: int, n_in: int, n_out: int,
         chol = chol.reshape(*lead, n_out, n_out)
         chol._psqrt_lower = True      # written by the kernel with an exactly zero upper triangle
     return F.reshape(*lead, n_out, n_in), chol, b.reshape(*lead, n_out)
+
+
+# ---- gradient path: forward-mode tangents (csrc/psqrt_tangent.cu; host driver psqrt/grad.py) ------------------
+def filter_smoother_tangent(ssm: LinearizedSSM, dssm: dict, y: torch.Tensor, fm, fL, sm=None, sL=None, dm0=None,
+                            dP0=None, *, smooth: bool = True, loglik: bool = True):
+    """psqrt_filter_smoother_tangent for one sequence.  `dssm`: {"dF", "dQ", "db", "dH", "dR", "dc"} -> tensor with the
+    entry's own shape (time-invariant) or a leading [T] axis, or None (zero); dQ / dR are COVARIANCE tangents.
+    (fm, fL, sm, sL): the primal trajectories of filter_smoother on the same inputs.
+    Returns (dfm [T+1,nx], dfP [T+1,nx,nx], dsm, dsP, dell) -- covariance tangents; dsm/dsP/dell None if not requested."""
+    lib = load()
+    T, ny = y.shape
+    nx = fm.shape[-1]
+    dev = y.device
+    keep = []
+    s = ssm.struct(T, 1, keep)
+    d = _SsmTangent()
+    for name, core in (("dF", (nx, nx)), ("dQ", (nx, nx)), ("db", (nx,)), ("dH", (ny, nx)), ("dR", (ny, ny)),
+                       ("dc", (ny,))):
+        t = dssm.get(name)
+        if t is None:
+            setattr(d, name, None)
+            continue
+        t = t.contiguous()
+        keep.append(t)
+        if tuple(t.shape) == core:
+            ts = 0
+        elif tuple(t.shape) == (T,) + core:
+            ts = int(np.prod(core))
+        else:
+            raise PsqrtError(f"{name}: shape {tuple(t.shape)} is neither {core} nor {(T,) + core}")
+        setattr(d, name, _ptr(t).value)
+        setattr(d, name + "_ts", ts)
+    nbytes = int(lib.psqrt_tangent_workspace_bytes(nx, ny, ctypes.c_int64(T)))
+    if nbytes == 0:
+        raise PsqrtError(f"psqrt_filter_smoother_tangent: unsupported nx={nx}, ny={ny}")
+    ws = workspace(nbytes, dev, slot=-1)
+    dfm = torch.empty((T + 1, nx), dtype=torch.float64, device=dev)
+    dfP = torch.empty((T + 1, nx, nx), dtype=torch.float64, device=dev)
+    dsm = torch.empty_like(dfm) if smooth else None
+    dsP = torch.empty_like(dfP) if smooth else None
+    dell = torch.empty((1,), dtype=torch.float64, device=dev) if loglik else None
+    args = [t.contiguous() if t is not None else None for t in (y, fm, fL, sm if smooth else None,
+                                                                  sL if smooth else None, dm0, dP0)]
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_filter_smoother_tangent(ctypes.byref(s), ctypes.byref(d), _ptr(args[0]), nx, ny,
+                                               ctypes.c_int64(T), _ptr(args[1]), _ptr(args[2]), _ptr(args[3]),
+                                               _ptr(args[4]), _ptr(args[5]), _ptr(args[6]), _ptr(dfm), _ptr(dfP),
+                                               _ptr(dsm), _ptr(dsP), _ptr(dell), ctypes.c_void_p(ws.data_ptr()),
+                                               ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_filter_smoother_tangent")
+    return dfm, dfP, dsm, dsP, (dell[0] if loglik else None)
+
+
+def cov_tangent_to_chol(L: torch.Tensor, dP: torch.Tensor) -> torch.Tensor:
+    """dL with d(L L^T) = dP for lower-triangular L [..., n, n]."""
+    lib = load()
+    n = L.shape[-1]
+    Lc, dPc = L.reshape(-1, n, n).contiguous(), dP.reshape(-1, n, n).contiguous()
+    dL = torch.empty_like(Lc)
+    with torch.cuda.device(L.device):
+        rc = lib.psqrt_cov_tangent_to_chol(_ptr(Lc), _ptr(dPc), _ptr(dL), n, ctypes.c_int64(Lc.shape[0]), _stream())
+    _check(rc, "psqrt_cov_tangent_to_chol")
+    return dL.reshape(L.shape)
+
+
+def linearize_builtin_tangent(model_id: int, params, dparams, lin_id: int, n_in: int, n_out: int, conditional: bool,
+                              nom_m, nom_L=None, dnom_m=None, dnom_L=None, dm_q=None, dQ_q=None, points=None):
+    """psqrt_linearize_builtin_tangent on [count, n] nominal means: -> (dF [count,d,n], dQ [count,d,d] or None, db)."""
+    lib = load()
+    dev = nom_m.device
+    m = nom_m.reshape(-1, n_in).contiguous()
+    count = m.shape[0]
+    dF = torch.empty((count, n_out, n_in), dtype=torch.float64, device=dev)
+    db = torch.empty((count, n_out), dtype=torch.float64, device=dev)
+    need_q = conditional or lin_id == LIN_SLR
+    dQ = torch.empty((count, n_out, n_out), dtype=torch.float64, device=dev) if need_q else None
+    L = dL = xi = wm = wc = None
+    P = 0
+    if lin_id == LIN_SLR:
+        L = nom_L.expand(count, n_in, n_in).contiguous()
+        dL = dnom_L.expand(count, n_in, n_in).contiguous() if dnom_L is not None else None
+        xi, wm, wc = _device_points(*points, dev)
+        P = xi.shape[0]
+    c = lambda t: t.contiguous() if t is not None else None
+    pars = (ctypes.c_double * len(params))(*[float(v) for v in params])
+    dpars = (ctypes.c_double * len(params))(*[float(v) for v in dparams]) if dparams is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_linearize_builtin_tangent(int(model_id), pars, dpars, int(lin_id), _ptr(xi), _ptr(wm), _ptr(wc),
+                                                 int(P), _ptr(m), _ptr(L), _ptr(c(dnom_m)), _ptr(dL),
+                                                 ctypes.c_int64(count), _ptr(c(dm_q)), _ptr(c(dQ_q)), _ptr(dF),
+                                                 _ptr(dQ), _ptr(db), _stream())
+    _check(rc, "psqrt_linearize_builtin_tangent")
+    return dF, dQ, db

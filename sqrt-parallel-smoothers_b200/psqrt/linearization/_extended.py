@@ -31,3 +31,8 @@ def linearize(model, x):
     m = x.mean
     res, F = value_and_jac(c_m, m)
     return F, apply_fn(c_chol, m), res - mv(F, m)
+
+
+# tags read by psqrt.grad (tangent of the linearization): the rule, and its unit sigma points if it has any
+linearize._psqrt_kind = "extended"
+linearize._psqrt_points = None

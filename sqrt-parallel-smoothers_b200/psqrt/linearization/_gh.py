@@ -55,3 +55,8 @@ def linearize(model, x, order: int = 3):
         f, q = model
         return linearize_functional(f, x, q, xi_t, wm_t, wc_t)
     return linearize_conditional(model[0], model[1], x, xi_t, wm_t, wc_t)
+
+
+# tags read by psqrt.grad (tangent of the linearization): the rule and its unit sigma points (wm, wc, xi)
+linearize._psqrt_kind = "slr"
+linearize._psqrt_points = lambda n, order=3: _gauss_hermite_weights(n, order)

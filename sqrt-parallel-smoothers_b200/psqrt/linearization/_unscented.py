@@ -43,3 +43,8 @@ def linearize(model, x, alpha: float = 1.0, beta: float = 0.0, kappa=None):
         f, q = model
         return linearize_functional(f, x, q, xi_t, wm_t, wc_t)
     return linearize_conditional(model[0], model[1], x, xi_t, wm_t, wc_t)
+
+
+# tags read by psqrt.grad (tangent of the linearization): the rule and its unit sigma points (wm, wc, xi)
+linearize._psqrt_kind = "slr"
+linearize._psqrt_points = lambda n, alpha=1.0, beta=0.0, kappa=None: _unscented_weights(n, alpha, beta, kappa)

@@ -71,3 +71,34 @@ def LLt(L):
 def rel_err(a, b):
     """max |a - b| / max |b|: error relative to the scale of the reference quantity."""
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def bearings_pe_case(T, seed, r_true=0.05, dt=0.01):
+    """Parameter-estimation variant of the bearings-only problem (notebooks/bearing_data_pe.py:123-146,
+    experiment_bearing_only_param_estimation_run_time.ipynb): first sensor's noise std r = 1 / prec is the
+    parameter, second sensor fixed at 0.1.  Data simulated with the coordinated-turn dynamics in float64; the
+    prior is centred near the truth so that the iterated smoothers converge in a few iterations."""
+    rng = np.random.RandomState(seed)
+    s1, s2 = np.array([-1.0, 0.5]), np.array([1.0, 1.0])
+    qc = qw = 0.1
+    x = np.array([0.1, 0.2, 1.0, 0.0, 1.0])
+    f = O.ct_transition_function(dt)
+    Q, _, _, _ = O.bearings_make_parameters(qc, qw, r_true, dt, s1, s2, r2=0.1)
+    cQ = np.linalg.cholesky(Q)
+    ys = np.zeros((T, 2))
+    for t in range(T):
+        x = f(x) + cQ @ rng.randn(5)
+        ys[t, 0] = np.arctan2(x[1] - s1[1], x[0] - s1[0]) + r_true * rng.randn()
+        ys[t, 1] = np.arctan2(x[1] - s2[1], x[0] - s2[0]) + 0.1 * rng.randn()
+    m0 = np.array([0.1, 0.2, 1.0, 0.0, 1.0]) + 0.05 * rng.randn(5)
+    L0 = np.diag([0.2, 0.2, 0.3, 0.3, 0.5])
+    return dict(ys=ys, m0=m0, L0=L0, s1=s1, s2=s2, qc=qc, qw=qw, dt=dt)
+
+
+def oracle_bearings_pe_models(case, prec):
+    """(transition_model, observation_model) at precision prec = 1 / r of the first sensor."""
+    Q, R, obs, trans = O.bearings_make_parameters(case["qc"], case["qw"], 1.0 / prec, case["dt"], case["s1"],
+                                                  case["s2"], r2=0.1)
+    tm = O.FunctionalModel(trans, O.MVNSqrt(np.zeros(5), np.linalg.cholesky(Q)))
+    om = O.FunctionalModel(obs, O.MVNSqrt(np.zeros(2), np.linalg.cholesky(R)))
+    return tm, om
