@@ -798,6 +798,65 @@ def run_bearings(args):
         def __getitem__(self, i):
             return ys_ds[mine.index(i)]
 
+    if args.grad:
+        # BASELINE.json configs[2]: log-likelihood + gradient path.  Protocol of
+        # notebooks/experiment_bearing_only_param_estimation_run_time.ipynb: parameter prec_r = 1 / r of the first
+        # sensor, R = diag(r^2, 0.1^2), value_and_grad of -ell through n_iter iterations of the iterated smoother
+        # (psqrt.grad.loglikelihood_jvp: n_iter primal passes + n_iter + 3 tangent passes on the device).
+        from psqrt import grad as pgrad
+        # the notebook's scenario: sensors, true start, noises, prior, initial nominal from the inverted bearings
+        s1g, s2g, qcg, qwg, r_true = np.array([-1.0, 0.5]), np.array([1.0, 1.0]), 0.1, 0.1, 0.05
+        _, _, ys_g = bearings.get_data_pe(np.array([0.1, 0.2, 1.0, 0.0]), dt, r_true, T, s1g, s2g, random_state=0)
+        ys_g = ys_g.astype(np.float64)
+        Qg, _, obs_g, trans_g = bearings.make_parameters(qcg, qwg, r_true, dt, s1g, s2g, r2=0.1)
+        tm = psqrt.FunctionalModel(trans_g, psqrt.MVNSqrt(np.zeros(5), np.linalg.cholesky(Qg)))
+        x0 = psqrt.MVNSqrt(np.array([2.0, 0.0, 0.0, 0.0, 0.0]), np.diag([0.5, 0.5, 0.5, 0.5, 1.0]))
+        pos = bearings.inverse_bearings(ys_g, s1g, s2g)
+        nom_m = np.concatenate([np.concatenate([np.zeros((1, 2)), pos], 0), np.zeros((T + 1, 3))], 1)
+        nominal = psqrt.MVNSqrt(g(nom_m), (np.sqrt(0.1) * torch.eye(5, dtype=torch.float64, device=dev)).expand(T + 1, 5, 5))
+        prec = args.prec
+        om_of = lambda p: psqrt.FunctionalModel(obs_g, psqrt.MVNSqrt(np.zeros(2), np.diag([1.0 / p, 0.1])))
+        om_pe = om_of(prec)
+        tg = pgrad.Tangents(observation_noise=psqrt.MVNSqrt(None, np.diag([-1.0 / prec ** 2, 0.0])))
+        ys_d = g(ys_g)
+
+        def run_grad():
+            return pgrad.loglikelihood_jvp(ys_d, x0, tm, om_pe, lin, tg, nominal, True,
+                                           criterion=lambda i, *_: i < n_iter)
+
+        for _ in range(max(args.warmup, 2)):
+            run_grad()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            nom, ell, dell = run_grad()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        # the primal alone, for the cost of the gradient relative to the value
+        e0.record()
+        for _ in range(args.steps):
+            psqrt.iterated_smoothing(ys_d, x0, tm, om_pe, lin, nominal, True, criterion=lambda i, *_: i < n_iter,
+                                     return_loglikelihood=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_val = e0.elapsed_time(e1) / args.steps
+        hfd = 1e-4 * prec   # check of the device gradient: central difference of the primal path itself
+        ells = [float(psqrt.iterated_smoothing(ys_d, x0, tm, om_of(prec + sgn * hfd), lin, nominal, True,
+                                               criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)[1])
+                for sgn in (1.0, -1.0)]
+        fd = (ells[0] - ells[1]) / (2 * hfd)
+        print(json.dumps({"workload": f"bearings-only CT nx=5 ny=2 T={T}, {args.lin} linearization, log-likelihood of the "
+                                      f"iterated sqrt parallel smoother ({n_iter} iterations) + d ell / d prec_r "
+                                      f"(BASELINE.json configs[2]; implicit fixed-point tangent, {n_iter + 2} Neumann terms)",
+                          "n_gpus": 1, "ms_per_value_and_grad": ms, "ms_per_value": ms_val,
+                          "tangent_passes": n_iter + 3, "ell": float(ell), "dell_dprec": float(dell),
+                          "dell_dprec_central_difference": fd, "prec_r": prec,
+                          "value": T * (2 * n_iter + 3) / (ms * 1e-3), "unit": "step-passes/s (primal + tangent)",
+                          "finite": bool(np.isfinite(float(ell)) and np.isfinite(float(dell)))}))
+        return 0
+
     def run():
         if args.batched and runs > 1:
             # config 5 through its driver: runs dealt round-robin, this rank's share smoothed as ONE batch per
@@ -860,6 +919,8 @@ def main():
     ap.add_argument("--lin", default="extended", choices=["extended", "cubature", "gauss_hermite", "unscented"])
     ap.add_argument("--runs", type=int, default=1, help="bearings workload: independent data sets smoothed in sequence")
     ap.add_argument("--batched", action="store_true", help="bearings workload: smooth the runs as one batch")
+    ap.add_argument("--grad", action="store_true", help="bearings workload: log-likelihood + gradient (configs[2])")
+    ap.add_argument("--prec", type=float, default=10.0, help="--grad: the parameter prec_r = 1 / r of the first sensor")
     ap.add_argument("--iters", type=int, default=10, help="bearings workload: iterations of the iterated smoother")
     ap.add_argument("--nx", type=int, default=4, help="state dimension of the LGSSM workload (informational runs; "
                                                       "the driver's metric is the default nx=4, ny=2)")

@@ -60,7 +60,22 @@ typedef struct psqrt_ssm {
    * steps and sequences (every stride 0) and its host mirrors are given, the sweeps carry the
    * model by value in their kernel parameters, i.e. as constant-bank operands. */
   const double *hF, *hcholQ, *hb, *hH, *hcholR, *hc;
+  /* Optional: a built-in model linearised INSIDE the sweeps (the per-step arrays are then never formed in HBM; this is
+   * the fused counterpart of psqrt_linearize_builtin + the pass, SURVEY 8b's psqrt_pass_fused).  fused_model =
+   * PSQRT_FUSED_CT_BEARINGS: coordinated-turn transition + two-bearings observation with the extended (first-order
+   * Taylor) linearization, nx = 5, ny = 2: step k uses F, b at nom_m[k] and H, c at nom_m[k + 1]
+   * (parallel/_filtering.py:103-104,117-119).  Then F, b, H, c are ignored (may be NULL); the noise is time-invariant
+   * and read from the HOST mirrors hcholQ [5,5] (lower), hb = m_q [5], hcholR [2,2], hc = m_r [2] (hcholR / hc may be
+   * NULL in smoother-only calls); fused_params (HOST) = {dt, s1x, s1y, s2x, s2y}; nom_m (DEVICE) [B, T+1, 5] with
+   * batch stride nom_bs (0 = shared).  Accepted by psqrt_filter_smoother and the staged calls
+   * (psqrt_filter_reduce / psqrt_filter_apply / psqrt_smoother_apply); PSQRT_EINVAL elsewhere. */
+  int32_t fused_model, fused_reserved;
+  const double* nom_m;
+  int64_t nom_bs;
+  const double* fused_params;
 } psqrt_ssm;
+#define PSQRT_FUSED_NONE 0
+#define PSQRT_FUSED_CT_BEARINGS 1
 
 typedef struct psqrt_plan {
   int32_t chunk_len;     /* K: consecutive steps handled by one thread                    */
@@ -216,6 +231,10 @@ int psqrt_sample_paths(const double* g, const double* E, const double* D, const 
 #define PSQRT_MODEL_POISSON_OBSERVATION 4
 #define PSQRT_LIN_EXTENDED 0
 #define PSQRT_LIN_SLR 1
+/* Non-finite entries per row of x [rows, row_len] -> counts [rows] (int64, device): the NaN-rate report of the robustness
+ * sweeps (notebooks/robustness_100runs.py:41-77 counts runs whose result is NaN). */
+int psqrt_count_nonfinite(const double* x, int64_t rows, int64_t row_len, int64_t* counts, void* stream);
+
 int psqrt_linearize_builtin(int model_id, const double* model_params, int lin_id, const double* xi,
                             const double* wm, const double* wc, int n_points, const double* nom_m,
                             const double* nom_L, int64_t count, const double* m_q, const double* chol_q,

@@ -4,6 +4,7 @@
 #include "../../include/psqrt.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "psqrt_kernels.cuh"
@@ -26,6 +27,16 @@ __global__ void __launch_bounds__(128) k_fp64_probe(double* out, int iters, doub
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += x[i];
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+k_count_nonfinite(const double* __restrict__ x, long long row_len, unsigned long long* __restrict__ counts) {
+  const long long row = blockIdx.y;
+  unsigned long long n = 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < row_len; i += (long long)gridDim.x * 256)
+    n += isfinite(x[row * row_len + i]) ? 0ull : 1ull;
+  n = __reduce_add_sync(0xffffffffu, (unsigned)n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counts + row, n);
 }
 
 void ell_sum(const double* ell_part, long long M, long long B, double* ell_out, cudaStream_t st) {
@@ -88,6 +99,7 @@ struct Ws {
       *ell_tmp;
   double* fpack;  // [B][K][nf_state][Ppad] packed filtered states handed from the forward to the backward sweep
   unsigned int *counter_f, *counter_s;
+  unsigned int* counter_x;  // [B][2] publish / ticket counters of the smoothing mid scan fused into K3
   size_t doubles;
 };
 Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B) {
@@ -113,13 +125,29 @@ Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B) {
   w.ell_tmp = take((size_t)B);
   w.counter_f = (unsigned int*)take((size_t)B);   // one 8-byte slot per sequence, used as uint32
   w.counter_s = (unsigned int*)take((size_t)B);
+  w.counter_x = (unsigned int*)take((size_t)B);   // two uint32 per sequence
   w.fpack = take((size_t)B * (size_t)p.chunk_len * (size_t)nf_state * (size_t)p.n_chunks_pad);
   w.doubles = off;
   return w;
 }
 
+// The fused-linearization description lives until this thread's next make_args call: every launch function copies it
+// into its kernel parameters before returning.
 SSMArgs make_args(const psqrt_ssm* s, const double* y, int ny, int64_t T) {
+  static thread_local psq::HostFused hf;
   SSMArgs a;
+  a.fused = nullptr;
+  if (s->fused_model == PSQRT_FUSED_CT_BEARINGS) {
+    for (int i = 0; i < 25; ++i) hf.Q[i] = s->hcholQ[i];
+    for (int i = 0; i < 5; ++i) hf.mq[i] = s->hb[i];
+    for (int i = 0; i < 4; ++i) hf.R[i] = s->hcholR ? s->hcholR[i] : 0.0;
+    for (int i = 0; i < 2; ++i) hf.mr[i] = s->hc ? s->hc[i] : 0.0;
+    hf.dt = s->fused_params[0];
+    hf.s1x = s->fused_params[1]; hf.s1y = s->fused_params[2];
+    hf.s2x = s->fused_params[3]; hf.s2y = s->fused_params[4];
+    hf.nom = s->nom_m; hf.nbs = s->nom_bs;
+    a.fused = &hf;
+  }
   a.F = s->F; a.Q = s->cholQ; a.bq = s->b; a.H = s->H; a.R = s->cholR; a.c = s->c; a.y = y;
   a.tF = s->F_ts; a.tQ = s->cholQ_ts; a.tb = s->b_ts; a.tH = s->H_ts; a.tR = s->cholR_ts; a.tc = s->c_ts;
   a.ty = ny;
@@ -155,8 +183,16 @@ psq::PeerCtx peer_ctx(const psqrt_peer* p) {
   return c;
 }
 
-bool ssm_ok(const psqrt_ssm* s, bool need_obs) {
-  if (!s || !s->F || !s->cholQ || !s->b) return false;
+// fused_dims: (nx, ny) of an entry point that accepts a fused built-in linearization ({0, 0}: it does not)
+bool ssm_ok(const psqrt_ssm* s, bool need_obs, int fused_nx = 0, int fused_ny = 0) {
+  if (!s) return false;
+  if (s->fused_model != PSQRT_FUSED_NONE) {
+    if (s->fused_model != PSQRT_FUSED_CT_BEARINGS || fused_nx != 5 || (need_obs && fused_ny != 2)) return false;
+    if (!s->nom_m || !s->fused_params || !s->hcholQ || !s->hb) return false;
+    if (need_obs && (!s->hcholR || !s->hc)) return false;
+    return true;
+  }
+  if (!s->F || !s->cholQ || !s->b) return false;
   if (need_obs && (!s->H || !s->cholR || !s->c)) return false;
   return true;
 }
@@ -228,7 +264,7 @@ size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, i
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
                         int chunk_len, double* ftotal, void* ws, size_t ws_bytes, const psqrt_peer* peer,
                         void* stream) {
-  if (!ssm_ok(ssm, true) || !y || ny <= 0) return PSQRT_EINVAL;
+  if (!ssm_ok(ssm, true, nx, ny) || !y || ny <= 0) return PSQRT_EINVAL;
   if (peer && !peer_ok(peer, batch)) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
@@ -238,7 +274,7 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   SSMArgs a = make_args(ssm, y, ny, T);
   HostModel hmv;
   c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_own,
-                       c.ws.chunk_pref, c.ws.warp_tot, c.ws.counter_f, st);
+                       c.ws.chunk_pref, c.ws.warp_tot, c.ws.counter_f, c.ws.counter_x, st);
   psq::PushArgs pa;
   memset(&pa, 0, sizeof(pa));
   if (peer) { pa.pc = peer_ctx(peer); pa.on = 1; }
@@ -266,7 +302,7 @@ int psqrt_carry_filter(const double* totals, int rank, int64_t batch, int nx, co
 int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carry_m, const double* carry_L, int nx,
                        int ny, int64_t T, int64_t batch, int chunk_len, double* fm, double* fL, double* ell,
                        double* stotal, void* ws, size_t ws_bytes, const psqrt_peer* peer, void* stream) {
-  if (!ssm_ok(ssm, true) || !y || ny <= 0 || !carry_m || !carry_L || !fm || !fL) return PSQRT_EINVAL;
+  if (!ssm_ok(ssm, true, nx, ny) || !y || ny <= 0 || !carry_m || !carry_L || !fm || !fL) return PSQRT_EINVAL;
   if (peer && (!peer_ok(peer, batch) || !stotal)) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
@@ -276,10 +312,18 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   SSMArgs a = make_args(ssm, y, ny, T);
   const int smooth = stotal != nullptr;
   HostModel hmv;
+  // Without a peer exchange and for a single sequence the smoothing mid scan (K4) runs inside K3 on a few extra
+  // CTAs, concurrently with the workers' step loops (psqrt_kernels.cuh, fused_smooth_mid); PSQRT_FUSE_MID=0: own kernel.
+  static const bool fuse_env = [] { const char* e = getenv("PSQRT_FUSE_MID"); return e ? atoi(e) != 0 : true; }();
+  const bool fuse = smooth && !peer && batch == 1 && fuse_env;
+  psq::FuseArgs fa;
+  fa.group_s = c.ws.group_s; fa.stotal = stotal; fa.ctr = fuse ? c.ws.counter_x : nullptr;
   c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m,
                       carry_L, c.ws.chunk_own, c.ws.chunk_pref, c.ws.warp_tot, c.ws.group_f, fm, fL, c.ws.chunk_suf,
-                      c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.fpack, st);
-  if (smooth) {
+                      c.ws.warp_stot, ell ? c.ws.ell_part : nullptr, c.ws.counter_s, c.ws.fpack, &fa, st);
+  if (fuse) {
+    if (ell) psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
+  } else if (smooth) {
     psq::PushArgs pa;
     memset(&pa, 0, sizeof(pa));
     if (peer) {
@@ -336,7 +380,7 @@ int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* f
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
                          double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
   (void)fm; (void)fL;  // identify the pass: psqrt_filter_apply left their packed copy in the workspace (psqrt.h)
-  if (!ssm_ok(ssm, false) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
+  if (!ssm_ok(ssm, false, nx, 0) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
@@ -489,6 +533,17 @@ extern "C" {
 // development aid (-DPSQ_MID_TRACE builds only; not declared in psqrt.h): out[2][128][16] %globaltimer stamps
 int psqrt_debug_trace(unsigned long long* out) { psq::mid_trace_read(out); return 0; }
 #endif
+
+int psqrt_count_nonfinite(const double* x, int64_t rows, int64_t row_len, int64_t* counts, void* stream) {
+  if (!x || !counts || rows <= 0 || rows > 65535 || row_len <= 0) return PSQRT_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(counts, 0, sizeof(int64_t) * (size_t)rows, st);
+  long long bx = (row_len + 256 * 8 - 1) / (256 * 8);
+  if (bx > 1024) bx = 1024;
+  psq::k_count_nonfinite<<<dim3((unsigned)bx, (unsigned)rows, 1), 256, 0, st>>>(
+      x, row_len, reinterpret_cast<unsigned long long*>(counts));
+  return check_launch();
+}
 
 int psqrt_fp64_probe(double* out, int iters, double* flops_out, void* stream) {
   if (!out || iters <= 0) return PSQRT_EINVAL;

@@ -21,6 +21,9 @@ const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
 }
 #else
 #include "psqrt_kernels.cuh"
+#if PSQ_N == 5
+#include "psqrt_fused.cuh"
+#endif
 #if !PSQ_MID2
 #include "psqrt_coop.cuh"
 #endif
@@ -57,6 +60,29 @@ SrcValT<NN> make_src_valT(const HostModel& h) {
   for (int i = 0; i < NN; ++i) s.m.bq[i] = h.bq[i];
   return s;
 }
+
+#if PSQ_N == 5
+inline void fill_fused(const HostFused& h, FusedCTBParams& p) {
+  for (int i = 0; i < 25; ++i) p.Q[i] = h.Q[i];
+  for (int i = 0; i < 5; ++i) p.mq[i] = h.mq[i];
+  for (int i = 0; i < 4; ++i) p.R[i] = h.R[i];
+  for (int i = 0; i < 2; ++i) p.mr[i] = h.mr[i];
+  p.dt = h.dt; p.s1x = h.s1x; p.s1y = h.s1y; p.s2x = h.s2x; p.s2y = h.s2y;
+}
+inline SrcFusedCTB make_src_fused(const SSMArgs& a) {
+  SrcFusedCTB s;
+  fill_fused(*a.fused, s.pr);
+  s.nom = a.fused->nom; s.nbs = a.fused->nbs;
+  s.y = a.y; s.ty = a.ty; s.sy = a.sy;
+  return s;
+}
+inline SrcFusedCT make_src_fusedT(const SSMArgs& a) {
+  SrcFusedCT s;
+  fill_fused(*a.fused, s.pr);
+  s.nom = a.fused->nom; s.nbs = a.fused->nbs;
+  return s;
+}
+#endif
 
 inline dim3 sweep_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kBlock), (unsigned)B, 1); }
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -107,37 +133,74 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 template <class KERN, class... Args>
-void launch_sweep(KERN kern, size_t smem, long long Ppad, long long B, cudaStream_t st, Args... args) {
+void launch_sweep_x(KERN kern, size_t smem, long long Ppad, long long B, int extra_ctas, cudaStream_t st, Args... args) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  launch_pdl(kern, sweep_grid(Ppad, B), dim3(kBlock, 1, 1), smem, st, 1, args...);
+  dim3 grid = sweep_grid(Ppad, B);
+  grid.x += (unsigned)extra_ctas;
+  launch_pdl(kern, grid, dim3(kBlock, 1, 1), smem, st, 1, args...);
+}
+template <class KERN, class... Args>
+void launch_sweep(KERN kern, size_t smem, long long Ppad, long long B, cudaStream_t st, Args... args) {
+  launch_sweep_x(kern, smem, Ppad, B, 0, st, args...);
+}
+// Extra CTAs appended to K3 for the fused smoothing mid scan (psqrt_kernels.cuh, fused_smooth_mid): what is left of the
+// sweeps' resident slots (2 CTAs per SM), at least 1 and at most 8.
+inline int fuse_extra_ctas(long long work_ctas) {
+  static const int slots = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * PSQ_MINB_K3;
+  }();
+  long long e = slots - work_ctas;
+  if (e < 1) e = 1;
+  if (e > 8) e = 8;
+  return (int)e;
 }
 
 template <int NY>
 struct NYImpl {
   static void filter_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                             double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter,
-                            cudaStream_t st) {
+                            unsigned int* fuse_ctr, cudaStream_t st) {
     const size_t ysmem = LaneRing<NY, kYDepth>::smem_bytes(kBlock);
+#if PSQ_N == 5
+    if constexpr (NY == 2) {
+      if (a.fused) {
+        launch_sweep(k_filter_reduce<N, NY, SrcFusedCTB>, ysmem, Ppad, B, st, make_src_fused(a), T, K, Ppad, chunk_own,
+                     chunk_pref, warp_tot, counter, fuse_ctr);
+        return;
+      }
+    }
+#endif
     if constexpr (kByValue) {
       if (hm) {
         launch_sweep(k_filter_reduce<N, NY, SrcVal<N, NY>>, ysmem, Ppad, B, st, make_src_val<NY>(*hm, a), T, K, Ppad,
-                     chunk_own, chunk_pref, warp_tot, counter);
+                     chunk_own, chunk_pref, warp_tot, counter, fuse_ctr);
         return;
       }
     }
     launch_sweep(k_filter_reduce<N, NY, SrcPtr>, ysmem, Ppad, B, st, SrcPtr{a}, T, K, Ppad, chunk_own, chunk_pref,
-                 warp_tot, counter);
+                 warp_tot, counter, fuse_ctr);
   }
   template <bool SMOOTH, bool LOGLIK, class SRC>
   static void filter_apply_t(const SRC& src, long long T, int K, long long Ppad, long long B, const double* cm,
                              const double* cL, const double* chunk_own, const double* chunk_pref,
                              const double* warp_pref, const double* group_pref, double* fm, double* fL,
                              double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
-                             double* fpack, cudaStream_t st) {
+                             double* fpack, const FuseArgs* fuse, cudaStream_t st) {
+    // fused smoothing mid scan: extra CTAs behind the workers (one sequence only: a batch orders its CTAs by sequence)
+    const bool fz = SMOOTH && fuse && fuse->ctr && B == 1;
+    const int n_work = fz ? (int)(Ppad / kBlock) : 0;
+    const int extra = fz ? fuse_extra_ctas(n_work) : 0;
+    double* const g_s = fz ? fuse->group_s : nullptr;
+    double* const tot_s = fz ? fuse->stotal : nullptr;
+    unsigned int* const fctr = fz ? fuse->ctr : nullptr;
 #define PSQ_K3(OUT)                                                                                                  \
-  launch_sweep(k_filter_apply<N, NY, SMOOTH, LOGLIK, SRC, OUT>, OUT::smem_bytes(kBlock) + LaneRing<NY, kYDepth>::smem_bytes(kBlock), Ppad, B, st, src, T, K, Ppad, cm, \
-               cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, counter_s, \
-               fpack)
+  launch_sweep_x(k_filter_apply<N, NY, SMOOTH, LOGLIK, SRC, OUT>,                                                    \
+                 OUT::smem_bytes(kBlock) + LaneRing<NY, kYDepth>::smem_bytes(kBlock), Ppad, B, extra, st, src, T, K, \
+                 Ppad, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL, chunk_suf, warp_stot, ell_part, \
+                 counter_s, fpack, n_work, g_s, tot_s, fctr)
     if constexpr (N % 2 == 0) {
       if (vec2_ok<N>(fm, fL)) { using O = WarpOut<N, 2>; PSQ_K3(O); return; }
     }
@@ -148,16 +211,25 @@ struct NYImpl {
                            long long B, const double* cm, const double* cL, const double* chunk_own,
                            const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
                            double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
-                           unsigned int* counter_s, double* fpack, cudaStream_t st) {
+                           unsigned int* counter_s, double* fpack, const FuseArgs* fuse, cudaStream_t st) {
 #define PSQ_FA(SM, SRCV)                                                                                             \
   do {                                                                                                               \
     if (ell_part)                                                                                                    \
       filter_apply_t<SM, true>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL,   \
-                               chunk_suf, warp_stot, ell_part, counter_s, fpack, st);                                \
+                               chunk_suf, warp_stot, ell_part, counter_s, fpack, fuse, st);                          \
     else                                                                                                             \
       filter_apply_t<SM, false>(SRCV, T, K, Ppad, B, cm, cL, chunk_own, chunk_pref, warp_pref, group_pref, fm, fL,  \
-                                chunk_suf, warp_stot, ell_part, counter_s, fpack, st);                               \
+                                chunk_suf, warp_stot, ell_part, counter_s, fpack, fuse, st);                         \
   } while (0)
+#if PSQ_N == 5
+    if constexpr (NY == 2) {
+      if (a.fused) {
+        const SrcFusedCTB sf = make_src_fused(a);
+        if (smooth) PSQ_FA(true, sf); else PSQ_FA(false, sf);
+        return;
+      }
+    }
+#endif
     if constexpr (kByValue) {
       if (hm) {
         const SrcVal<N, NY> sv = make_src_val<NY>(*hm, a);
@@ -335,6 +407,13 @@ void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, lon
                   const double* cm, const double* cL, long long cms, long long cLs, const double* chunk_suf,
                   const double* warp_suf, const double* group_suf, const double* fpack, double* sm, double* sL,
                   int write_terminal, cudaStream_t st) {
+#if PSQ_N == 5
+  if (a.fused) {
+    smooth_apply_t(make_src_fusedT(a), T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm, sL,
+                   write_terminal, st);
+    return;
+  }
+#endif
   if constexpr (kByValue) {
     if (hm) {
       smooth_apply_t(make_src_valT<N>(*hm), T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm,

@@ -45,10 +45,12 @@ constexpr int kXDepth = 2;       // packed filtered states of the backward sweep
 
 // Linearised SSM as the kernels see it: base pointers + per-step and per-sequence strides in
 // doubles (0 = shared by all steps / all sequences).
+struct HostFused;   // psqrt_launch.h: fused built-in linearization (psqrt_fused.cuh), host side
 struct SSMArgs {
   const double *F, *Q, *bq, *H, *R, *c, *y;
   long long tF, tQ, tb, tH, tR, tc, ty;  // time strides
   long long sF, sQ, sb, sH, sR, sc, sy;  // sequence (batch) strides
+  const HostFused* fused;                // HOST pointer, read by the launch code only (nullptr: model arrays above)
 };
 
 __device__ __forceinline__ StepPtrs step_ptrs(const SSMArgs& a, long long seq, long long k) {
@@ -297,13 +299,20 @@ struct WarpOut {
 template <int N, int NY, class SRC>
 __global__ void __launch_bounds__(kBlock, PSQ_MINB_K1)
 k_filter_reduce(const __grid_constant__ SRC src, long long T, int K, long long Ppad, double* __restrict__ chunk_own,
-                double* __restrict__ chunk_pref, double* __restrict__ warp_tot, unsigned int* __restrict__ counter) {
+                double* __restrict__ chunk_pref, double* __restrict__ warp_tot, unsigned int* __restrict__ counter,
+                unsigned int* __restrict__ fuse_ctr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
   pdl_entry();
-  if (c == 0) counter[seq] = 0u;  // arms the ticket of the mid-level scan that follows
+  if (c == 0) {
+    counter[seq] = 0u;  // arms the ticket of the mid-level scan that follows
+    if (fuse_ctr) {     // and the publish / ticket counters of the smoothing mid scan fused into K3
+      fuse_ctr[2 * seq] = 0u;
+      fuse_ctr[2 * seq + 1] = 0u;
+    }
+  }
   FAcc<N> acc;
   acc.set_identity();
   const long long k0 = c * K;
@@ -513,6 +522,102 @@ k_mid_scan(double* __restrict__ items, long long M, double* __restrict__ groups,
 }
 
 // =========================================================================================
+// K4 fused into K3.  The smoothing warp totals exist ~20 us into K3 (right after the once-per-chunk prologue) while
+// K3 goes on for another ~65 us filtering through its chunks, and the sweeps leave a few CTA slots of the GPU empty
+// (290 CTAs on 148 x 2 slots at T = 1e6).  A handful of extra CTAs appended to K3's grid wait until every worker warp
+// has published its total, then run the two-level suffix scan of K4 (one warp per group of IT totals, the warp that
+// takes the last ticket scans the group totals) concurrently with the workers' step loops: the mid-scan latency
+// leaves the critical path and K4's launch disappears.  Workers never wait for the scan CTAs, so the scheme cannot
+// deadlock whatever the block scheduler does; if the extra CTAs only get a slot when workers retire, the scan simply
+// starts late.  ctr[0]: published warp totals, ctr[1]: ticket; both zeroed by K1 of the same pass.
+// =========================================================================================
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int N>
+__device__ __noinline__ void fused_smooth_mid(double* __restrict__ items, long long M, double* __restrict__ groups,
+                                              unsigned int* __restrict__ ctr, double* __restrict__ total_out,
+                                              long long seq, int sw, int nsw) {
+  using Elem = SElem<N>;
+  constexpr int IT = MidCfg<N>::IT;
+  constexpr int PER = IT / 32;   // consecutive items (scan order) per lane
+  const int lane = threadIdx.x & 31;
+  const long long Gc = (M + IT - 1) / IT;
+  if (lane == 0) {
+    while (ld_acquire_u32(ctr) < (unsigned int)M) __nanosleep(256);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (long long g = sw; g < Gc; g += nsw) {
+    Elem it[PER];
+    Elem acc;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const long long sidx = g * IT + (long long)lane * PER + q;
+      it[q].set_identity();
+      if (sidx < M) soa_load_cg(items, seq, M, M - 1 - sidx, it[q]);
+      if (q == 0) {
+        acc = it[0];
+      } else {
+        Elem c2 = ScanOp<Elem>::combine(acc, it[q]);
+        if (sidx < M) acc = c2;
+      }
+    }
+    Elem incl = warp_scan_inclusive<Elem, false>(acc, lane);
+    Elem run = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const long long sidx = g * IT + (long long)lane * PER + q;
+      if (sidx < M) soa_store(items, seq, M, M - 1 - sidx, run);
+      if (q + 1 < PER) run = ScanOp<Elem>::combine(run, it[q]);
+    }
+    if (lane == 31) soa_store(groups, seq, Gc, g, incl);
+  }
+  __threadfence();
+  unsigned int ticket = 0u;
+  if (lane == 0) ticket = atomicAdd(ctr + 1, 1u);
+  ticket = __shfl_sync(kFull, ticket, 0);
+  if (ticket != (unsigned int)(nsw - 1)) return;
+  __threadfence();
+  // this warp finished last: exclusive scan of the Gc group totals, lane l owning q consecutive ones
+  const int q = (int)((Gc + 31) / 32);
+  const long long s0 = (long long)lane * q;
+  Elem acc;
+  acc.set_identity();
+#pragma unroll 1
+  for (int i = 0; i < q; ++i) {
+    Elem x;
+    x.set_identity();
+    if (s0 + i < Gc) soa_load_cg(groups, seq, Gc, s0 + i, x);
+    if (i == 0) {
+      acc = x;
+    } else {
+      Elem c2 = ScanOp<Elem>::combine(acc, x);
+      if (s0 + i < Gc) acc = c2;
+    }
+  }
+  Elem incl = warp_scan_inclusive<Elem, false>(acc, lane);
+  Elem run = warp_exclusive_from_inclusive<Elem, false>(incl, lane);
+  if (lane == 31 && total_out) {
+#pragma unroll
+    for (int f = 0; f < Elem::NF; ++f) total_out[seq * Elem::NF + f] = incl.v[f];
+  }
+#pragma unroll 1
+  for (int i = 0; i < q; ++i) {
+    Elem x;
+    x.set_identity();
+    if (s0 + i < Gc) {
+      soa_load_cg(groups, seq, Gc, s0 + i, x);
+      soa_store(groups, seq, Gc, s0 + i, run);
+    }
+    if (i + 1 < q) run = ScanOp<Elem>::combine(run, x);
+  }
+}
+
+// =========================================================================================
 // K3
 // =========================================================================================
 template <int N, int NY, bool SMOOTH, bool LOGLIK, class SRC, class OUT>
@@ -523,7 +628,11 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
                const double* __restrict__ warp_pref, const double* __restrict__ group_pref,
                double* __restrict__ fm, double* __restrict__ fL,  // [B][T+1][N], [B][T+1][N][N]; index k+1 written
                double* __restrict__ chunk_suf, double* __restrict__ warp_stot, double* __restrict__ ell_part,
-               unsigned int* __restrict__ counter, double* __restrict__ fpack) {
+               unsigned int* __restrict__ counter, double* __restrict__ fpack,
+               // fused smoothing mid scan (fused_smooth_mid above): n_work = worker CTAs in x (0: not fused; the CTAs
+               // beyond them run the scan), its group array, sequence total (or null) and counters
+               int n_work, double* __restrict__ group_s, double* __restrict__ stotal,
+               unsigned int* __restrict__ fuse_ctr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const long long seq = blockIdx.y;
   const long long c = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -533,6 +642,14 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
   const long long k1 = (k0 + K < T) ? k0 + K : T;
 
   pdl_entry();
+  if constexpr (SMOOTH) {
+    if (n_work > 0 && (int)blockIdx.x >= n_work) {
+      const int nsw = ((int)gridDim.x - n_work) * (kBlock / 32);
+      const int sw = ((int)blockIdx.x - n_work) * (kBlock / 32) + (threadIdx.x >> 5);
+      fused_smooth_mid<N>(warp_stot, Mw, group_s, fuse_ctr + 2 * seq, stotal, seq, sw, nsw);
+      return;
+    }
+  }
   if (SMOOTH && c == 0) counter[seq] = 0u;
   LaneRing<NY, kYDepth> yring(smem_raw + OUT::smem_bytes(kBlock));
 #pragma unroll
@@ -567,7 +684,13 @@ k_filter_apply(const __grid_constant__ SRC src, long long T, int K, long long Pp
     SElem<N> incl = warp_scan_inclusive<SElem<N>, true>(sacc, lane);
     SElem<N> excl = warp_exclusive_from_inclusive<SElem<N>, true>(incl, lane);
     soa_store(chunk_suf, seq, Ppad, c, excl);
-    if (lane == 0) soa_store(warp_stot, seq, Mw, c / 32, incl);
+    if (lane == 0) {
+      soa_store(warp_stot, seq, Mw, c / 32, incl);
+      if (n_work > 0) {   // publish to the scan CTAs
+        __threadfence();
+        atomicAdd(fuse_ctr + 2 * seq, 1u);
+      }
+    }
   }
   // The step loop runs K + 1 times in every lane of a warp that has any work (the cooperative writes
   // need the whole warp); lanes past the end of the sequence idle through it.  Inside the chunk the

@@ -15,14 +15,32 @@ struct HostModel {
   const double *F, *Q, *bq, *H, *R, *c;
 };
 
+// Built-in model linearised inside the sweeps (psqrt_fused.cuh; psqrt_ssm.fused_* in include/psqrt.h): coordinated
+// turn + two bearings, extended linearization, nx = 5, ny = 2.  All host data except `nom` (device).
+struct HostFused {
+  double Q[25], mq[5], R[4], mr[2];
+  double dt, s1x, s1y, s2x, s2y;
+  const double* nom;   // [B][T + 1][5] nominal means (device)
+  long long nbs;       // batch stride of nom, 0 = shared
+};
+
+// Smoothing mid scan fused into K3 (psqrt_kernels.cuh, fused_smooth_mid): its group array, the sequence total (or
+// null) and the two counters per sequence that K1 zeroes.  ctr == nullptr: K4 runs as its own kernel.
+struct FuseArgs {
+  double* group_s;
+  double* stotal;
+  unsigned int* ctr;
+};
+
 struct LaunchNY {
   void (*filter_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
-                        double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter, cudaStream_t);
+                        double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter,
+                        unsigned int* fuse_ctr, cudaStream_t);
   void (*filter_apply)(int smooth, const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                        const double* carry_m, const double* carry_L, const double* chunk_own,
                        const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
                        double* fL, double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
-                       double* fpack, cudaStream_t);
+                       double* fpack, const FuseArgs* fuse, cudaStream_t);
   void (*filter_elements)(const SSMArgs&, long long T, long long B, const double* m0, const double* L0, double* A,
                           double* b, double* U, double* eta, double* Z, cudaStream_t);
   void (*loglik_terms)(const SSMArgs&, long long T, long long B, const double* fm, const double* fL, double* terms,

@@ -28,7 +28,12 @@ class _Ssm(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("F", "cholQ", "b", "H", "cholR", "c")] + \
                [(n, ctypes.c_int64) for n in ("F_ts", "cholQ_ts", "b_ts", "H_ts", "cholR_ts", "c_ts")] + \
                [(n, ctypes.c_int64) for n in ("F_bs", "cholQ_bs", "b_bs", "H_bs", "cholR_bs", "c_bs")] + \
-               [(n, ctypes.c_void_p) for n in ("hF", "hcholQ", "hb", "hH", "hcholR", "hc")]
+               [(n, ctypes.c_void_p) for n in ("hF", "hcholQ", "hb", "hH", "hcholR", "hc")] + \
+               [("fused_model", ctypes.c_int32), ("fused_reserved", ctypes.c_int32), ("nom_m", ctypes.c_void_p),
+                ("nom_bs", ctypes.c_int64), ("fused_params", ctypes.c_void_p)]
+
+
+FUSED_CT_BEARINGS = 1
 
 
 class Peer(ctypes.Structure):
@@ -57,7 +62,7 @@ EXPORTS = (
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
     "psqrt_fp64_probe", "psqrt_peer_layout", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
     "psqrt_tangent_workspace_bytes", "psqrt_filter_smoother_tangent", "psqrt_cov_tangent_to_chol",
-    "psqrt_linearize_builtin_tangent",
+    "psqrt_linearize_builtin_tangent", "psqrt_count_nonfinite",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -185,9 +190,35 @@ class LinearizedSSM:
     def __init__(self, F, cholQ, b, H=None, cholR=None, c=None, host=None):
         self.F, self.cholQ, self.b, self.H, self.cholR, self.c = F, cholQ, b, H, cholR, c
         self.host = dict(host or {})
+        self.fused = None
+
+    @classmethod
+    def fused_ct_bearings(cls, nom_mean: torch.Tensor, params, cholQ, m_q, cholR=None, m_r=None):
+        """The built-in bearings-only model linearised (extended) INSIDE the sweeps (psqrt_ssm.fused_model,
+        csrc/psqrt_fused.cuh): nom_mean [T+1, 5] or [B, T+1, 5] device tensor; params = (dt, s1x, s1y, s2x, s2y) and the
+        time-invariant noise (cholQ lower [5,5], m_q [5], cholR [2,2], m_r [2]) as HOST arrays."""
+        obj = cls(None, None, None)
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        obj.fused = dict(nom=nom_mean.contiguous(), params=f64(params), cholQ=f64(cholQ), m_q=f64(m_q), cholR=f64(cholR),
+                         m_r=f64(m_r))
+        return obj
 
     def struct(self, T: int, batch: int, keep: list) -> _Ssm:
         s = _Ssm()
+        if self.fused is not None:
+            fz = self.fused
+            nom = fz["nom"]
+            if nom.shape[-2:] != (T + 1, 5) or nom.dim() not in (2, 3) or (nom.dim() == 3 and nom.shape[0] != batch):
+                raise PsqrtError(f"fused model: nominal means {tuple(nom.shape)} do not match T + 1 = {T + 1}, nx = 5")
+            keep.extend([nom] + [v for k, v in fz.items() if k != "nom" and v is not None])
+            s.fused_model = FUSED_CT_BEARINGS
+            s.nom_m = _ptr(nom).value
+            s.nom_bs = (T + 1) * 5 if nom.dim() == 3 else 0
+            s.fused_params = fz["params"].ctypes.data
+            s.hcholQ, s.hb = fz["cholQ"].ctypes.data, fz["m_q"].ctypes.data
+            if fz["cholR"] is not None:
+                s.hcholR, s.hc = fz["cholR"].ctypes.data, fz["m_r"].ctypes.data
+            return s
         for name, core in (("F", 2), ("cholQ", 2), ("b", 1), ("H", 2), ("cholR", 2), ("c", 1)):
             t = getattr(self, name)
             if t is None:
@@ -729,3 +760,17 @@ def linearize_builtin_tangent(model_id: int, params, dparams, lin_id: int, n_in:
                                                  _ptr(dQ), _ptr(db), _stream())
     _check(rc, "psqrt_linearize_builtin_tangent")
     return dF, dQ, db
+
+
+def count_nonfinite(x: torch.Tensor) -> torch.Tensor:
+    """Non-finite entries per leading index of x [rows, ...] -> int64 [rows] (psqrt_count_nonfinite): the NaN-rate
+    report of the robustness sweeps (notebooks/robustness_100runs.py:41-77)."""
+    lib = load()
+    rows = x.shape[0]
+    xc = x.reshape(rows, -1).contiguous()
+    counts = torch.empty((rows,), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.psqrt_count_nonfinite(_ptr(xc), ctypes.c_int64(rows), ctypes.c_int64(xc.shape[1]),
+                                       ctypes.c_void_p(counts.data_ptr()), _stream())
+    _check(rc, "psqrt_count_nonfinite")
+    return counts

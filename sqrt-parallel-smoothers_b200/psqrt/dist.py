@@ -348,3 +348,10 @@ def iterated_smoothing_batch_sharded(observations, x0: MVNSqrt, transition_model
         if ids:
             ell_all[ids] = gathered[r, :len(ids)]
     return idx, local_nominal, ell_all
+
+
+def nonfinite_runs(trajectory: MVNSqrt) -> torch.Tensor:
+    """[B] bool: the runs of a batch [B, T + 1, ...] whose trajectory contains a NaN or Inf -- the failure count the
+    robustness sweeps report (notebooks/robustness_100runs.py:41-77); counted on the device (psqrt_count_nonfinite)."""
+    from . import _lib
+    return (_lib.count_nonfinite(trajectory.mean) + _lib.count_nonfinite(trajectory.chol)) > 0

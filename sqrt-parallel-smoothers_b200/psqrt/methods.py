@@ -9,6 +9,7 @@ Same names, positional order and return conventions as the reference.  What diff
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -92,8 +93,46 @@ def _lower(chol):
     return out
 
 
-def _linearize(lin, transition_model, observation_model, nominal):
+_FUSE_LIN_DEFAULT = "0"   # see DESIGN.md section 5 (measured A/B)
+
+
+def _host_mirror(t):
+    """The private host copy _t attached to a tensor it built from host data, if still valid."""
+    h = getattr(t, "_psqrt_host", None)
+    if h is None or getattr(t, "_psqrt_host_version", None) != t._version:
+        return None
+    return h
+
+
+def _fused_ssm(lin, transition_model, observation_model, nominal):
+    """The built-in bearings-only model with the extended linearization is linearised INSIDE the sweeps
+    (csrc/psqrt_fused.cuh): no per-step (F, b, H, c) arrays are formed.  Needs the time-invariant noise on the host
+    (mirrors kept by _t for inputs that came from host data) and a lower-triangular cholQ; None = not applicable.
+    PSQRT_FUSE_LIN=0 turns it off."""
+    if os.environ.get("PSQRT_FUSE_LIN", _FUSE_LIN_DEFAULT) == "0" or getattr(lin, "_psqrt_kind", None) != "extended":
+        return None
+    if not (isinstance(transition_model, FunctionalModel) and isinstance(observation_model, FunctionalModel)):
+        return None
+    bt = getattr(transition_model.function, "_psqrt_builtin", None)
+    bo = getattr(observation_model.function, "_psqrt_builtin", None)
+    if getattr(bt, "model_id", None) != _lib.MODEL_CT_TRANSITION or \
+            getattr(bo, "model_id", None) != _lib.MODEL_BEARINGS_OBSERVATION:
+        return None
+    if not nominal.mean.is_cuda or nominal.mean.dim() != 2:
+        return None
+    hq = [_host_mirror(t) for t in (transition_model.mvn.chol, transition_model.mvn.mean, observation_model.mvn.chol,
+                                    observation_model.mvn.mean)]
+    if any(h is None for h in hq) or np.any(np.triu(hq[0], 1)):
+        return None
+    return LinearizedSSM.fused_ct_bearings(nominal.mean, list(bt.params) + list(bo.params), hq[0], hq[1], hq[2], hq[3])
+
+
+def _linearize(lin, transition_model, observation_model, nominal, fused_ok=False):
     """transition at nominal[:-1], observation at nominal[1:] (parallel/_filtering.py:103-104,117-119)."""
+    if fused_ok and observation_model is not None:
+        ssm = _fused_ssm(lin, transition_model, observation_model, nominal)
+        if ssm is not None:
+            return ssm
     F, cholQ, b = lin(transition_model, _slice(nominal, slice(None, -1)))
     cholQ = _lower(cholQ)
     if observation_model is None:
@@ -130,7 +169,7 @@ def _run(observations, x0, transition_model, observation_model, lin, nominal, sm
         nominal = _mvn(nominal, dev)
     else:
         nominal = _default_nominal(T + 1, nx, dev)
-    ssm = _linearize(lin, transition_model, observation_model, nominal)
+    ssm = _linearize(lin, transition_model, observation_model, nominal, fused_ok=True)
     fm, fL, sm, sL, ell = _lib.filter_smoother(ssm, ys, x0.mean, _prior_factor(x0.chol), smooth=smooth,
                                                loglik=loglik)
     # index 0 of the filtered trajectory is x0 itself (parallel/_filtering.py:45-46)

@@ -96,7 +96,24 @@ def make_parameters(qc, qw, r, dt, s1, s2, r2=None):
     return Q, R, make_observation_function(s1, s2), make_transition_function(dt)
 
 
-def get_data(x0, dt, r, T, s1, s2, q=10.0, random_state=None):
+def inverse_bearings(observations, s1, s2):
+    """Positions as if the two bearings were noise-free (notebooks/bearing_data_pe.py:68-90): the initial linearization
+    points of the parameter-estimation experiments.  observations [..., 2] -> [..., 2]."""
+    ys = np.asarray(observations, dtype=np.float64)
+    t1, t2 = np.tan(ys[..., 0]), np.tan(ys[..., 1])
+    b1, b2 = s1[0] * t1 - s1[1], s2[0] * t2 - s2[1]
+    # [[t1, -1], [t2, -1]] p = [b1, b2]
+    px = (b1 - b2) / (t1 - t2)
+    return np.stack([px, t1 * px - b1], -1)
+
+
+def get_data_pe(x0, dt, r, T, s1, s2, q=10.0, random_state=None, r2=0.1):
+    """Parameter-estimation variant (notebooks/bearing_data_pe.py:137-198): first sensor's noise std r, second
+    sensor's fixed at r2 = 0.1."""
+    return get_data(x0, dt, r, T, s1, s2, q=q, random_state=random_state, r2=r2)
+
+
+def get_data(x0, dt, r, T, s1, s2, q=10.0, random_state=None, r2=None):
     """Simulated trajectory + bearings (procedure of notebooks/bearing_data.py:137-198, float32
     like the reference; the closed-form matrix exponential of the turn replaces scipy.linalg.expm)."""
     if random_state is None or isinstance(random_state, int):
@@ -120,7 +137,7 @@ def get_data(x0, dt, r, T, s1, s2, q=10.0, random_state=None):
         E = np.array([[1, 0, sa, ca1], [0, 1, -ca1, sa], [0, 0, c, s], [0, 0, -s, c]], dtype=np.float32)
         x = E @ x
         y1 = np.arctan2(x[1] - s1[1], x[0] - s1[0]) + r * normals[i, 0]
-        y2 = np.arctan2(x[1] - s2[1], x[0] - s2[0]) + r * normals[i, 1]
+        y2 = np.arctan2(x[1] - s2[1], x[0] - s2[0]) + (r if r2 is None else r2) * normals[i, 1]
         observations[i] = [y1, y2]
         true_states[i + 1] = np.concatenate((x, np.array([a], dtype=np.float32)))
     return ts, true_states, observations
