@@ -98,11 +98,12 @@ struct Ws {
   double *chunk_own, *chunk_pref, *warp_tot, *group_f, *ftotal, *chunk_suf, *warp_stot, *group_s, *stotal, *ell_part,
       *ell_tmp;
   double* fpack;  // [B][K][nf_state][Ppad] packed filtered states handed from the forward to the backward sweep
+  double* trig;   // [B][T + 1][4] transcendental values of a fused built-in linearization (psqrt_fused.cuh)
   unsigned int *counter_f, *counter_s;
   unsigned int* counter_x;  // [B][2] publish / ticket counters of the smoothing mid scan fused into K3
   size_t doubles;
 };
-Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B) {
+Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B, int64_t T) {
   Ws w;
   double* d = (double*)base;
   size_t off = 0;
@@ -127,6 +128,7 @@ Ws carve(void* base, const psqrt_plan& p, int nf_state, int64_t B) {
   w.counter_s = (unsigned int*)take((size_t)B);
   w.counter_x = (unsigned int*)take((size_t)B);   // two uint32 per sequence
   w.fpack = take((size_t)B * (size_t)p.chunk_len * (size_t)nf_state * (size_t)p.n_chunks_pad);
+  w.trig = take(nf_state == 20 ? (size_t)B * (size_t)(T + 1) * 4 : 0);   // nx = 5 only (nf_state = 5 + 15)
   w.doubles = off;
   return w;
 }
@@ -167,6 +169,14 @@ const HostModel* host_model(const psqrt_ssm* s, bool need_obs, HostModel* out) {
   out->F = s->hF; out->Q = s->hcholQ; out->bq = s->hb;
   out->H = need_obs ? s->hH : nullptr; out->R = need_obs ? s->hcholR : nullptr; out->c = need_obs ? s->hc : nullptr;
   return out;
+}
+
+// workspace part of a fused built-in linearization (the HostFused behind a.fused is this thread's, see make_args)
+void bind_fused(const SSMArgs& a, const Ws& w, int64_t T) {
+  if (!a.fused) return;
+  psq::HostFused* h = const_cast<psq::HostFused*>(a.fused);
+  h->trig = w.trig;
+  h->tbs = (long long)(T + 1) * 4;
 }
 
 int check_launch() { return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA; }
@@ -215,7 +225,7 @@ int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws,
   if (B > 65535) return PSQRT_EINVAL;
   int rc = make_plan(c.ln, T, B, chunk_len, &c.plan);
   if (rc) return rc;
-  c.ws = carve(ws, c.plan, c.ln->nf_state, B);
+  c.ws = carve(ws, c.plan, c.ln->nf_state, B, T);
   if (!ws || ws_bytes < c.ws.doubles * sizeof(double)) return PSQRT_EWORKSPACE;
   return PSQRT_OK;
 }
@@ -258,7 +268,7 @@ size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, i
   const LaunchN* ln = table_for(nx);
   psqrt_plan p;
   if (!ln || make_plan(ln, T, batch, chunk_len, &p)) return 0;
-  return carve(nullptr, p, ln->nf_state, batch).doubles * sizeof(double);
+  return carve(nullptr, p, ln->nf_state, batch, T).doubles * sizeof(double);
 }
 
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
@@ -272,6 +282,11 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   if (peer && peer->payload != c.ln->nf_filter) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
+  bind_fused(a, c.ws, T);
+  if (a.fused) {   // the transcendental values of every nominal point, once per pass (the later stages reuse them)
+    if (!c.ln->fused_prepare) return PSQRT_EUNSUPPORTED;
+    c.ln->fused_prepare(a, T, batch, st);
+  }
   HostModel hmv;
   c.lny->filter_reduce(a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_own,
                        c.ws.chunk_pref, c.ws.warp_tot, c.ws.counter_f, c.ws.counter_x, st);
@@ -310,6 +325,7 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   if (peer && peer->payload != c.ln->nf_smoother + nx + (int64_t)nx * nx) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, y, ny, T);
+  bind_fused(a, c.ws, T);
   const int smooth = stotal != nullptr;
   HostModel hmv;
   // Without a peer exchange and for a single sequence the smoothing mid scan (K4) runs inside K3 on a few extra
@@ -385,6 +401,7 @@ int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* f
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
+  bind_fused(a, c.ws, T);
   HostModel hmv;
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L,
                      nx, (long long)nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL,
@@ -407,6 +424,7 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
   if (rc || !smooth) return rc;
   // terminal carry = filtered state at index T of every sequence
   SSMArgs a = make_args(ssm, nullptr, 0, T);
+  bind_fused(a, c.ws, T);
   HostModel hmv;
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
                      fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,

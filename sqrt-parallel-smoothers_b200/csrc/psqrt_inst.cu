@@ -73,6 +73,7 @@ inline SrcFusedCTB make_src_fused(const SSMArgs& a) {
   SrcFusedCTB s;
   fill_fused(*a.fused, s.pr);
   s.nom = a.fused->nom; s.nbs = a.fused->nbs;
+  s.trig = a.fused->trig; s.tbs = a.fused->tbs;
   s.y = a.y; s.ty = a.ty; s.sy = a.sy;
   return s;
 }
@@ -80,7 +81,13 @@ inline SrcFusedCT make_src_fusedT(const SSMArgs& a) {
   SrcFusedCT s;
   fill_fused(*a.fused, s.pr);
   s.nom = a.fused->nom; s.nbs = a.fused->nbs;
+  s.trig = a.fused->trig; s.tbs = a.fused->tbs;
   return s;
+}
+void fused_prepare(const SSMArgs& a, long long T, long long B, cudaStream_t st) {
+  const HostFused& h = *a.fused;
+  k_fused_trig<<<dim3((unsigned)((T + 1 + 127) / 128), (unsigned)B, 1), 128, 0, st>>>(h.dt, h.s1x, h.s1y, h.s2x, h.s2y,
+                                                                                    h.nom, h.nbs, T + 1, h.trig);
 }
 #endif
 
@@ -495,6 +502,11 @@ const LaunchN kTable = {N,
                         &escan_smooth_apply,
                         &filter_combine,
                         &smooth_combine,
+#if PSQ_N == 5
+                        &fused_prepare,
+#else
+                        nullptr,
+#endif
                         &tria,
                         &chol_update};
 

@@ -22,6 +22,8 @@ struct HostFused {
   double dt, s1x, s1y, s2x, s2y;
   const double* nom;   // [B][T + 1][5] nominal means (device)
   long long nbs;       // batch stride of nom, 0 = shared
+  double* trig;        // [B][T + 1][4] workspace: transcendental values per nominal point (k_fused_trig)
+  long long tbs;       // (T + 1) * 4
 };
 
 // Smoothing mid scan fused into K3 (psqrt_kernels.cuh, fused_smooth_mid): its group array, the sequence total (or
@@ -86,6 +88,8 @@ struct LaunchN {
                          long long n, double* A, double* b, double* U, double* eta, double* Z, cudaStream_t);
   void (*smooth_combine)(const double* g1, const double* E1, const double* D1, const double* g2, const double* E2,
                          const double* D2, long long n, double* g, double* E, double* D, cudaStream_t);
+  // fused built-in linearization (nx = 5 only, else nullptr): fills HostFused::trig for the pass
+  void (*fused_prepare)(const SSMArgs&, long long T, long long B, cudaStream_t);
   void (*tria)(const double* A, double* L, int cols, long long batch, cudaStream_t);
   void (*chol_update)(double* L, const double* V, int k, double alpha, long long batch, cudaStream_t);
 };

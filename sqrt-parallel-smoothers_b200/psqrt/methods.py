@@ -93,7 +93,7 @@ def _lower(chol):
     return out
 
 
-_FUSE_LIN_DEFAULT = "0"   # see DESIGN.md section 5 (measured A/B)
+_FUSE_LIN_DEFAULT = "1"   # bearings T = 1e5 x 10 iterations: 2.8-3.2 ms fused, 3.45-3.6 ms unfused
 
 
 def _host_mirror(t):

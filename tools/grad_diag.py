@@ -13,6 +13,7 @@ g = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, devi
 lin = getattr(psqrt.linearization, sys.argv[1] if len(sys.argv) > 1 else "extended")
 qdata = float(sys.argv[2]) if len(sys.argv) > 2 else 10.0
 sx = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0     # sensors at (-sx, 0.5), (sx, 1.0)
+init = sys.argv[4] if len(sys.argv) > 4 else "inverse"    # initial nominal: inverted bearings | truth + noise
 for T in (1000, 10000, 100000):
     dt, r_true = 0.01, 0.05
     s1, s2 = np.array([-sx, 0.5]), np.array([sx, 1.0])
@@ -23,6 +24,9 @@ for T in (1000, 10000, 100000):
     x0 = psqrt.MVNSqrt(np.array([2.0, 0.0, 0.0, 0.0, 0.0]), np.diag([0.5, 0.5, 0.5, 0.5, 1.0]))
     pos = bearings.inverse_bearings(ys, s1, s2)
     nom_m = np.concatenate([np.concatenate([np.zeros((1, 2)), pos], 0), np.zeros((T + 1, 3))], 1)
+    if init == "truth":
+        nom_m = xs.astype(np.float64) + 0.1 * np.random.RandomState(1).randn(T + 1, 5)
+        x0 = psqrt.MVNSqrt(np.array([0.1, 0.2, 1.0, 0.0, 1.0]), np.diag([0.5, 0.5, 0.5, 0.5, 1.0]))
     nominal = psqrt.MVNSqrt(g(nom_m), (np.sqrt(0.1) * torch.eye(5, dtype=torch.float64, device=dev)).expand(T + 1, 5, 5).contiguous())
     prec = 10.0
     om_of = lambda p: psqrt.FunctionalModel(obs_f, psqrt.MVNSqrt(np.zeros(2), np.diag([1.0 / p, 0.1])))
