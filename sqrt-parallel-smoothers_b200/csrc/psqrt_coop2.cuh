@@ -464,7 +464,7 @@ k_mid_scan2(double* __restrict__ items, long long M, double* __restrict__ groups
   auto slot = [&](int s, int xx) { return slots + (s * IT + xx) * NFD; };
 
   PSQ_TRACE(REV, 0);
-  if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
+  for (int f = threadIdx.x; f < NF; f += blockDim.x) dmap[f] = OP::dense_of(f);
   for (int k = threadIdx.x; k < (2 * IT + 1) * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
   pdl_entry();                                         // shared-memory set-up overlaps the predecessor's tail
   __syncthreads();
@@ -674,7 +674,7 @@ k_carry_scan(const double* __restrict__ totals, int first, int step, int count, 
   const int x = threadIdx.x / G;
   double* const ws = wsall + x * OP::WS;
   auto slot = [&](int s, int xx) { return slots + (s * IT + xx) * NFD; };
-  if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
+  for (int f = threadIdx.x; f < NF; f += blockDim.x) dmap[f] = OP::dense_of(f);
   for (int k = threadIdx.x; k < 2 * IT * NFD; k += blockDim.x) slots[k] = 0.0;
   if (use_peer) {
     // every rank has published pass number `epoch` for this sequence (all ranks, not only the ones whose totals
@@ -802,7 +802,7 @@ k_mid_scan3(double* __restrict__ items, long long M, double* __restrict__ groups
   auto slot = [&](int s, int xx) { return slots + (s * IC + xx) * NFD; };
 
   PSQ_TRACE(REV, 0);
-  if (threadIdx.x < NF) dmap[threadIdx.x] = OP::dense_of(threadIdx.x);
+  for (int f = threadIdx.x; f < NF; f += blockDim.x) dmap[f] = OP::dense_of(f);
   for (int k = threadIdx.x; k < 3 * IC * NFD; k += blockDim.x) slots[k] = 0.0;   // upper triangles stay zero
   pdl_entry();                                         // shared-memory set-up overlaps the predecessor's tail
   __syncthreads();

@@ -297,7 +297,7 @@ void launch_mid2(double* items, long long M, long long B, double* groups, unsign
 }
 // Cluster form (psqrt_coop2.cuh, k_mid_scan3): the IT = 64 items of a group spread over a cluster of CS CTAs on CS SMs.
 // PSQRT_MID_CLUSTER: bit 0 = filtering scan, bit 1 = smoothing scan (default below; 0 = single-CTA groups everywhere).
-constexpr bool kClusterMid = (PSQ_N <= 4);
+constexpr bool kClusterMid = (PSQ_N <= 8);
 constexpr int kClusterDefault = 1;
 inline int cluster_mask() {
   static const int m = [] {

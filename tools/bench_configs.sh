@@ -15,6 +15,9 @@ done
 python bench.py --workload bearings --lin extended --T 10000 --runs 100 --iters 20 --steps 2 --warmup 1 2>&1 | tail -1 > gpurun_out/configs_c5_bearings_100runs_T1e4.json
 python bench.py --workload bearings --lin extended --T 10000 --runs 100 --iters 20 --batched --steps 3 --warmup 1 2>&1 | tail -1 > gpurun_out/configs_c5_bearings_100runs_T1e4_batched.json
 python bench.py --workload bearings --lin unscented --steps 5 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c2_bearings_unscented.json
+for lin in extended cubature gauss_hermite; do
+  python bench.py --workload bearings --grad --lin $lin --steps 3 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c3_grad_$lin.json
+done
 python - <<'PY'
 import glob, json
 for p in sorted(glob.glob("gpurun_out/configs_*.json")):
