@@ -194,7 +194,7 @@ int psqrt_smoother_combine(const double* g1, const double* E1, const double* D1,
 
 /* ---- math utilities (parsmooth/_utils.py) ------------------------------------------------
  * psqrt_tria_batched        _utils.py:22-24: A [batch, rows, cols] -> L [batch, rows, rows] lower
- *                           triangular with L L^T = A A^T (rows <= 8, any cols >= 1)
+ *                           triangular with L L^T = A A^T (rows <= 16, any cols >= 1; rows in {1..6, 8} tuned)
  * psqrt_chol_update_batched _utils.py:13-19,39-81: L [batch,n,n] <- chol(L L^T + alpha sum_k v_k v_k^T),
  *                           V [batch,k,n], sequential over k, non-finite entries -> 0 */
 int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t batch, void* stream);
@@ -273,6 +273,31 @@ int psqrt_linearize_builtin_tangent(int model_id, const double* model_params, co
                                     const double* nom_m, const double* nom_L, const double* dnom_m,
                                     const double* dnom_L, int64_t count, const double* dm_q, const double* dQ_q,
                                     double* dF, double* dQ, double* db, void* stream);
+
+/* ---- generic path: any nx <= 16, ny <= 16, fp64 or fp32 (csrc/psqrt_generic.cu) -----------------------------
+ * A literal statement of the reference's algorithm -- elements (parallel/_filtering.py:100-146, _smoothing.py:47-85),
+ * operators (parallel/_operators.py:43-125) and the associative scan as a Hillis-Steele scan over element arrays in
+ * HBM -- with runtime dimensions, one thread per time step; O(T log T) combines, nothing tuned.  It backs
+ *   - psqrt_filter_smoother / psqrt_smoother / psqrt_workspace_bytes / psqrt_tria_batched / psqrt_chol_update_batched
+ *     for the dimensions the tuned kernels do not cover (psqrt_supported() == 0): they fall back to it on their own;
+ *   - the float32 mode of the robustness experiments (notebooks/robustness_100runs.py:7,41-77):
+ *     psqrt_filter_smoother_f32, all arrays float, time_strides / batch_strides [6] in ELEMENTS for
+ *     (F, cholQ, b, H, cholR, c), ell accumulated in double.
+ * psqrt_filter_smoother_generic takes the arguments of psqrt_filter_smoother (y == NULL: smoother only, fm / fL are then
+ * inputs; sm == sL == NULL: filter only); L0 and cholQ may be any square-root factors.  The staged, seam, sampler and
+ * tangent entry points have no generic form.  Workspace: psqrt_generic_workspace_bytes(nx, T, batch, fp32). */
+int psqrt_supported_generic(int nx, int ny);
+size_t psqrt_generic_workspace_bytes(int nx, int64_t T, int64_t batch, int fp32);
+int psqrt_filter_smoother_generic(const psqrt_ssm* ssm, const double* y, const double* m0, const double* L0, int nx,
+                                  int ny, int64_t T, int64_t batch, double* fm, double* fL, double* sm, double* sL,
+                                  double* ell, void* ws, size_t ws_bytes, void* stream);
+int psqrt_filter_smoother_f32(const float* F, const float* cholQ, const float* b, const float* H, const float* cholR,
+                              const float* c, const int64_t* time_strides, const int64_t* batch_strides,
+                              const float* y, const float* m0, const float* L0, int nx, int ny, int64_t T,
+                              int64_t batch, float* fm, float* fL, float* sm, float* sL, double* ell, void* ws,
+                              size_t ws_bytes, void* stream);
+int psqrt_tria_generic(const double* A, double* L, int rows, int cols, int64_t batch, void* stream);
+int psqrt_chol_update_generic(double* L, const double* V, int n, int k, double alpha, int64_t batch, void* stream);
 
 /* ---- measurement aid (bench.py): FP64 FMA throughput probe ------------------------------------
  * Launches 148 x 4 CTAs of 128 threads, each thread running 8 independent chains of `iters` x 16 dependent

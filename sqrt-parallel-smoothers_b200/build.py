@@ -133,7 +133,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
         if n not in NX_LIST:
             defs.append("-DPSQ_STUB")       # launch table symbol only, no kernels
         units.append((inst, os.path.join(BUILD, f"inst_n{n}_{_digest(inst, ' '.join(defs))}.o"), defs))
-    for name in ("psqrt_capi.cu", "psqrt_models.cu", "psqrt_sampler.cu", "psqrt_tangent.cu"):
+    for name in ("psqrt_capi.cu", "psqrt_models.cu", "psqrt_sampler.cu", "psqrt_tangent.cu", "psqrt_generic.cu"):
         src = os.path.join(CSRC, name)
         if os.path.exists(src):
             units.append((src, os.path.join(BUILD, f"{name[6:-3]}_{_digest(src, '')}.o"), []))

@@ -179,6 +179,18 @@ void bind_fused(const SSMArgs& a, const Ws& w, int64_t T) {
   h->tbs = (long long)(T + 1) * 4;
 }
 
+// Dimensions the tuned kernels cover; everything else up to 16 goes to the generic path (psqrt_generic.cu).
+// PSQRT_FORCE_GENERIC=1 sends the whole-pass entry points there for every dimension (tests, A/B).
+bool force_generic() {
+  static const bool f = [] { const char* e = getenv("PSQRT_FORCE_GENERIC"); return e && atoi(e) != 0; }();
+  return f;
+}
+bool tuned_dims(int nx, int ny) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln) return false;
+  return ny == 0 || ln->for_ny(ny) != nullptr;
+}
+
 int check_launch() { return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA; }
 
 bool peer_ok(const psqrt_peer* p, int64_t batch) {
@@ -263,12 +275,13 @@ int psqrt_get_plan(int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqr
 }
 
 size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, int chunk_len) {
-  (void)op;
-  (void)ny;
+  const size_t gen = (op == PSQRT_OP_FILTER_SMOOTHER) ? psqrt_generic_workspace_bytes(nx, T, batch, 0) : 0;
+  if (!tuned_dims(nx, ny)) return gen;   // served by the generic path (0 if it cannot either)
   const LaunchN* ln = table_for(nx);
   psqrt_plan p;
-  if (!ln || make_plan(ln, T, batch, chunk_len, &p)) return 0;
-  return carve(nullptr, p, ln->nf_state, batch, T).doubles * sizeof(double);
+  if (make_plan(ln, T, batch, chunk_len, &p)) return 0;
+  const size_t tuned = carve(nullptr, p, ln->nf_state, batch, T).doubles * sizeof(double);
+  return (force_generic() && gen > tuned) ? gen : tuned;
 }
 
 int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, int64_t batch,
@@ -413,6 +426,8 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
                           int64_t T, int64_t batch, int chunk_len, double* fm, double* fL, double* sm, double* sL,
                           double* ell, void* ws, size_t ws_bytes, void* stream) {
   if (!m0 || !L0 || !fm || !fL || ((sm == nullptr) != (sL == nullptr))) return PSQRT_EINVAL;
+  if ((!tuned_dims(nx, ny) || force_generic()) && ssm && ssm->fused_model == PSQRT_FUSED_NONE)
+    return psqrt_filter_smoother_generic(ssm, y, m0, L0, nx, ny, T, batch, fm, fL, sm, sL, ell, ws, ws_bytes, stream);
   Ctx c;
   int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
@@ -436,6 +451,9 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
 int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int nx, int64_t T, int64_t batch,
                    int chunk_len, double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
   if (!ssm_ok(ssm, false) || !fm || !fL || !sm || !sL) return PSQRT_EINVAL;
+  if (!tuned_dims(nx, 0) || force_generic())
+    return psqrt_filter_smoother_generic(ssm, nullptr, nullptr, nullptr, nx, 0, T, batch, const_cast<double*>(fm),
+                                         const_cast<double*>(fL), sm, sL, nullptr, ws, ws_bytes, stream);
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
   if (rc) return rc;
@@ -538,7 +556,7 @@ int psqrt_smoother_combine(const double* g1, const double* E1, const double* D1,
 
 int psqrt_tria_batched(const double* A, double* L, int rows, int cols, int64_t batch, void* stream) {
   const LaunchN* ln = table_for(rows);
-  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (!ln) return (rows >= 1 && rows <= 16) ? psqrt_tria_generic(A, L, rows, cols, batch, stream) : PSQRT_EUNSUPPORTED;
   if (!A || !L || cols <= 0 || batch <= 0) return PSQRT_EINVAL;
   ln->tria(A, L, cols, batch, (cudaStream_t)stream);
   return check_launch();
@@ -573,7 +591,7 @@ int psqrt_fp64_probe(double* out, int iters, double* flops_out, void* stream) {
 
 int psqrt_chol_update_batched(double* L, const double* V, int n, int k, double alpha, int64_t batch, void* stream) {
   const LaunchN* ln = table_for(n);
-  if (!ln) return PSQRT_EUNSUPPORTED;
+  if (!ln) return (n >= 1 && n <= 16) ? psqrt_chol_update_generic(L, V, n, k, alpha, batch, stream) : PSQRT_EUNSUPPORTED;
   if (!L || !V || k < 0 || batch <= 0) return PSQRT_EINVAL;
   ln->chol_update(L, V, k, alpha, batch, (cudaStream_t)stream);
   return check_launch();

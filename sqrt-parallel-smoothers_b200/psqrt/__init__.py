@@ -6,7 +6,7 @@ the numerics run in hand-written sm_100a CUDA kernels (libpsqrt.so) behind a C A
 """
 from ._base import MVNStandard, MVNSqrt, FunctionalModel, ConditionalMomentsModel, are_inputs_compatible
 from .methods import filtering, smoothing, filter_smoother, iterated_smoothing, sampling
-from . import grad, linearization, methods, models
+from . import fp32, grad, linearization, methods, models
 
 __all__ = ["MVNStandard", "MVNSqrt", "FunctionalModel", "ConditionalMomentsModel", "are_inputs_compatible",
-           "filtering", "smoothing", "filter_smoother", "iterated_smoothing", "sampling", "linearization", "methods", "models", "grad"]
+           "filtering", "smoothing", "filter_smoother", "iterated_smoothing", "sampling", "linearization", "methods", "models", "grad", "fp32"]

@@ -62,7 +62,9 @@ EXPORTS = (
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
     "psqrt_fp64_probe", "psqrt_peer_layout", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
     "psqrt_tangent_workspace_bytes", "psqrt_filter_smoother_tangent", "psqrt_cov_tangent_to_chol",
-    "psqrt_linearize_builtin_tangent", "psqrt_count_nonfinite",
+    "psqrt_linearize_builtin_tangent", "psqrt_count_nonfinite", "psqrt_supported_generic",
+    "psqrt_generic_workspace_bytes", "psqrt_filter_smoother_generic", "psqrt_filter_smoother_f32", "psqrt_tria_generic",
+    "psqrt_chol_update_generic",
 )
 
 MODEL_CT_TRANSITION, MODEL_BEARINGS_OBSERVATION, MODEL_RICKER_TRANSITION, MODEL_POISSON_OBSERVATION = 1, 2, 3, 4
@@ -90,6 +92,8 @@ def load() -> ctypes.CDLL:
                                           ctypes.c_int]
     lib.psqrt_get_plan.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                    ctypes.POINTER(Plan)]
+    lib.psqrt_generic_workspace_bytes.restype = ctypes.c_size_t
+    lib.psqrt_generic_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
     lib.psqrt_tangent_workspace_bytes.restype = ctypes.c_size_t
     lib.psqrt_tangent_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64]
     lib.psqrt_peer_layout.restype = ctypes.c_int64
@@ -169,10 +173,17 @@ def get_plan(nx: int, ny: int, T: int, batch: int = 1, chunk_len: int = 0) -> Pl
     return p
 
 
-def _require(nx: int, ny: int):
-    if not supported(nx, ny):
-        raise PsqrtError(f"libpsqrt.so has no kernels for nx={nx}, ny={ny} "
-                         f"(compiled: nx in 1,2,3,4,5,6,8 and ny in 1..4)")
+def supported_generic(nx: int, ny: int = 0) -> bool:
+    return bool(load().psqrt_supported_generic(int(nx), int(ny)))
+
+
+def _require(nx: int, ny: int, generic_ok: bool = False):
+    """Tuned kernels: nx in {1,2,3,4,5,6,8}, ny in 1..4.  The whole-pass calls (`generic_ok`) fall back to the generic
+    path of csrc/psqrt_generic.cu for any nx, ny <= 16 inside the library."""
+    if supported(nx, ny) or (generic_ok and supported_generic(nx, ny)):
+        return
+    raise PsqrtError(f"libpsqrt.so has no kernels for nx={nx}, ny={ny} (tuned: nx in 1,2,3,4,5,6,8 and ny in 1..4; "
+                     f"generic whole-pass path: nx, ny <= 16)")
 
 
 class LinearizedSSM:
@@ -272,16 +283,17 @@ def _batchify(x: torch.Tensor, core: int):
 
 
 def filter_smoother(ssm: LinearizedSSM, y: torch.Tensor, m0: torch.Tensor, L0: torch.Tensor, *, smooth: bool = True,
-                    loglik: bool = False, chunk_len: int = 0):
+                    loglik: bool = False, chunk_len: int = 0, generic: bool = False):
     """One pass.  y [T, ny] or [B, T, ny]; m0 [nx] / [B, nx]; L0 lower-triangular [nx, nx] / [B, nx, nx].
-    Returns (fm, fL, sm, sL, ell) with sm/sL/ell None when not requested."""
+    Returns (fm, fL, sm, sL, ell) with sm/sL/ell None when not requested.  Dimensions outside the tuned set run on
+    the library's generic path (nx, ny <= 16); `generic=True` forces that path (psqrt_filter_smoother_generic)."""
     lib = load()
     yb, had_b = _batchify(y, 2)
     B, T, ny = yb.shape
     m0b, _ = _batchify(m0, 1)
     L0b, _ = _batchify(L0, 2)
     nx = m0b.shape[-1]
-    _require(nx, ny)
+    _require(nx, ny, generic_ok=True)
     if m0b.shape[0] != B:
         m0b = m0b.expand(B, nx)
         L0b = L0b.expand(B, nx, nx)
@@ -292,16 +304,26 @@ def filter_smoother(ssm: LinearizedSSM, y: torch.Tensor, m0: torch.Tensor, L0: t
     sm = torch.empty_like(fm) if smooth else None
     sL = torch.empty_like(fL) if smooth else None
     ell = torch.empty((B,), dtype=torch.float64, device=dev) if loglik else None
-    nbytes = lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len)
-    ws = workspace(nbytes, dev)
     keep = []
     s = ssm.struct(T, B, keep)
-    with torch.cuda.device(dev):
-        rc = lib.psqrt_filter_smoother(ctypes.byref(s), _ptr(yb), _ptr(m0b), _ptr(L0b), nx, ny,
-                                       ctypes.c_int64(T), ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(sm),
-                                       _ptr(sL), _ptr(ell), ctypes.c_void_p(ws.data_ptr()),
-                                       ctypes.c_size_t(ws.numel()), _stream())
-    _check(rc, "psqrt_filter_smoother")
+    if generic:
+        nbytes = int(lib.psqrt_generic_workspace_bytes(nx, ctypes.c_int64(T), ctypes.c_int64(B), 0))
+        ws = workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            rc = lib.psqrt_filter_smoother_generic(ctypes.byref(s), _ptr(yb), _ptr(m0b), _ptr(L0b), nx, ny,
+                                                   ctypes.c_int64(T), ctypes.c_int64(B), _ptr(fm), _ptr(fL), _ptr(sm),
+                                                   _ptr(sL), _ptr(ell), ctypes.c_void_p(ws.data_ptr()),
+                                                   ctypes.c_size_t(ws.numel()), _stream())
+        _check(rc, "psqrt_filter_smoother_generic")
+    else:
+        nbytes = lib.psqrt_workspace_bytes(0, nx, ny, T, B, chunk_len)
+        ws = workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            rc = lib.psqrt_filter_smoother(ctypes.byref(s), _ptr(yb), _ptr(m0b), _ptr(L0b), nx, ny,
+                                           ctypes.c_int64(T), ctypes.c_int64(B), chunk_len, _ptr(fm), _ptr(fL), _ptr(sm),
+                                           _ptr(sL), _ptr(ell), ctypes.c_void_p(ws.data_ptr()),
+                                           ctypes.c_size_t(ws.numel()), _stream())
+        _check(rc, "psqrt_filter_smoother")
     if not had_b:
         fm, fL = fm[0], fL[0]
         sm, sL = (sm[0], sL[0]) if smooth else (None, None)
@@ -316,7 +338,7 @@ def smoother(ssm: LinearizedSSM, fm: torch.Tensor, fL: torch.Tensor, *, chunk_le
     fmb, fLb = fmb.contiguous(), fLb.contiguous()
     B, Tp1, nx = fmb.shape
     T = Tp1 - 1
-    _require(nx, 0)
+    _require(nx, 0, generic_ok=True)
     sm, sL = torch.empty_like(fmb), torch.empty_like(fLb)
     if T == 0:
         sm.copy_(fmb)
@@ -774,3 +796,45 @@ def count_nonfinite(x: torch.Tensor) -> torch.Tensor:
                                        ctypes.c_void_p(counts.data_ptr()), _stream())
     _check(rc, "psqrt_count_nonfinite")
     return counts
+
+
+def filter_smoother_f32(F, cholQ, b, H, cholR, c, y, m0, L0, *, smooth: bool = True, loglik: bool = False):
+    """psqrt_filter_smoother_f32: the pass in float32 (generic path; notebooks/robustness_100runs.py runs the square-root
+    smoother in float32).  Model entries: float32 CUDA tensors with their own shape (time-invariant) or a leading [T]
+    axis; y [T, ny]; one sequence.  Returns (fm, fL, sm, sL, ell) -- float32 trajectories, ell a float64 scalar."""
+    lib = load()
+    T, ny = y.shape
+    nx = m0.shape[-1]
+    dev = y.device
+    core = {"F": (nx, nx), "cholQ": (nx, nx), "b": (nx,), "H": (ny, nx), "cholR": (ny, ny), "c": (ny,)}
+    arrs, ts = [], []
+    for name, t in (("F", F), ("cholQ", cholQ), ("b", b), ("H", H), ("cholR", cholR), ("c", c)):
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(t.shape) == core[name]:
+            ts.append(0)
+        elif tuple(t.shape) == (T,) + core[name]:
+            ts.append(int(np.prod(core[name])))
+        else:
+            raise PsqrtError(f"{name}: shape {tuple(t.shape)} is neither {core[name]} nor {(T,) + core[name]}")
+        arrs.append(t)
+    f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+    y32, m032, L032 = f32(y), f32(m0), f32(L0)
+    fm = torch.empty((T + 1, nx), dtype=torch.float32, device=dev)
+    fL = torch.empty((T + 1, nx, nx), dtype=torch.float32, device=dev)
+    sm = torch.empty_like(fm) if smooth else None
+    sL = torch.empty_like(fL) if smooth else None
+    ell = torch.empty((1,), dtype=torch.float64, device=dev) if loglik else None
+    nbytes = int(lib.psqrt_generic_workspace_bytes(nx, ctypes.c_int64(T), ctypes.c_int64(1), 1))
+    if nbytes == 0:
+        raise PsqrtError(f"psqrt_filter_smoother_f32: unsupported nx={nx}")
+    ws = workspace(nbytes, dev, slot=-2)
+    p32 = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    ts_arr = (ctypes.c_int64 * 6)(*ts)
+    bs_arr = (ctypes.c_int64 * 6)(0, 0, 0, 0, 0, 0)
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_filter_smoother_f32(*[p32(t) for t in arrs], ts_arr, bs_arr, p32(y32), p32(m032), p32(L032), nx,
+                                           ny, ctypes.c_int64(T), ctypes.c_int64(1), p32(fm), p32(fL), p32(sm),
+                                           p32(sL), _ptr(ell), ctypes.c_void_p(ws.data_ptr()),
+                                           ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_filter_smoother_f32")
+    return fm, fL, sm, sL, (ell[0] if loglik else None)

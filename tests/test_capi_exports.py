@@ -37,11 +37,17 @@ def test_host_side_queries():
     p1 = _lib.get_plan(5, 2, 7, 1, 3)
     assert (p1.chunk_len, p1.n_chunks) == (3, 3)
     assert lib.psqrt_workspace_bytes(0, 4, 2, 1_000_000, 1, 0) > 0
-    assert lib.psqrt_workspace_bytes(0, 7, 2, 1000, 1, 0) == 0           # unsupported nx
+    # nx = 7 has no tuned kernels: the whole-pass op is served by the generic path, the element scan is not
+    assert lib.psqrt_workspace_bytes(0, 7, 2, 1000, 1, 0) == lib.psqrt_generic_workspace_bytes(7, 1000, 1, 0) > 0
+    assert lib.psqrt_workspace_bytes(1, 7, 2, 1000, 1, 0) == 0
+    assert lib.psqrt_workspace_bytes(0, 17, 2, 1000, 1, 0) == 0          # beyond the generic path too
+    assert _lib.supported_generic(7, 2) and _lib.supported_generic(16, 16) and not _lib.supported_generic(17, 1)
     # argument validation happens before any launch
     s = _lib._Ssm()
     rc = lib.psqrt_filter_smoother(ctypes.byref(s), None, None, None, 4, 2, ctypes.c_int64(10), ctypes.c_int64(1), 0,
                                    None, None, None, None, None, None, ctypes.c_size_t(0), None)
     assert rc == -1
-    rc = lib.psqrt_tria_batched(None, None, 7, 3, ctypes.c_int64(1), None)
+    rc = lib.psqrt_tria_batched(None, None, 7, 3, ctypes.c_int64(1), None)     # rows = 7: generic path, validates too
+    assert rc == -1
+    rc = lib.psqrt_tria_batched(None, None, 17, 3, ctypes.c_int64(1), None)    # beyond both paths
     assert rc == -2
