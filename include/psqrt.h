@@ -268,6 +268,16 @@ int psqrt_filter_smoother_tangent(const psqrt_ssm* ssm, const psqrt_ssm_tangent*
                                   const double* dm0, const double* dP0, double* dfm, double* dfP, double* dsm,
                                   double* dsP, double* dell, void* ws, size_t ws_bytes, void* stream);
 int psqrt_cov_tangent_to_chol(const double* L, const double* dP, double* dL, int n, int64_t count, void* stream);
+/* Reverse mode for the log-likelihood at a fixed linearised model: d ell / d (every entry of the model), all steps at
+ * once, for the cost of about one tangent pass.  The costates (lam_k, Lam_k) = d ell / d (m_k, P_k) obey the transposed
+ * affine recursion backwards in time (again an associative scan of matrix products); they are written to lam [T+1,nx],
+ * Lam [T+1,nx,nx] (index 0 = gradient w.r.t. the prior mean / covariance), and contracted per step into
+ *   gF [T,nx,nx], gb [T,nx], gH [T,ny,nx], gc [T,ny]   and, in COVARIANCE form,   gQ [T,nx,nx], gR [T,ny,ny]
+ * (d ell = <gQ, dQ> for symmetric dQ; w.r.t. a factor: 2 gQ cholQ).  fm, fL: the primal filtered trajectory of
+ * psqrt_filter_smoother.  Workspace: psqrt_tangent_workspace_bytes.  One sequence. */
+int psqrt_loglik_adjoint(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, const double* fm,
+                         const double* fL, double* lam, double* Lam, double* gF, double* gQ, double* gb, double* gH,
+                         double* gR, double* gc, void* ws, size_t ws_bytes, void* stream);
 int psqrt_linearize_builtin_tangent(int model_id, const double* model_params, const double* dmodel_params, int lin_id,
                                     const double* xi, const double* wm, const double* wc, int n_points,
                                     const double* nom_m, const double* nom_L, const double* dnom_m,

@@ -168,6 +168,90 @@ __device__ void apply(const Map<N>& a, double (&dm)[N], double (&dP)[N][N]) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The ADJOINT family (reverse mode, psqrt_loglik_adjoint): costates (lam, Lam) = d ell / d (m_k, P_k) obey the transposed
+// recursion backwards in time,
+//     lam_k = Phi^T lam_{k+1} + w,     Lam_k = Phi^T Lam_{k+1} Phi + sym((Phi^T lam_{k+1}) w^T) + B,
+// again closed under composition; a Map holds (P = Psi, w = v, C = D; c unused):
+//     lam = Psi^T lam' + v,   Lam = Psi^T Lam' Psi + sym((Psi^T lam') v^T) + D.
+// ------------------------------------------------------------------------------------------------
+// out = G_b o G_a for a = LATER steps (applied first going backwards), b = EARLIER step(s)
+template <int N>
+__device__ void compose_adj(const Map<N>& a, const Map<N>& b, Map<N>& out) {
+  double t[N];   // b.P^T a.w
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = fma(b.P[j][i], a.w[j], s);
+    t[i] = s;
+    out.c[i] = 0.0;
+  }
+  double AC[N][N];   // a.C b.P
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0, p = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) { s = fma(a.C[i][k], b.P[k][j], s); p = fma(a.P[i][k], b.P[k][j], p); }
+      AC[i][j] = s;
+      out.P[i][j] = p;
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    out.w[i] = b.w[i] + t[i];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double q = b.C[i][j] + 0.5 * (t[i] * b.w[j] + t[j] * b.w[i]);
+#pragma unroll
+      for (int k = 0; k < N; ++k) q = fma(b.P[k][i], AC[k][j], q);
+      out.C[i][j] = q;
+    }
+  }
+}
+// (lam, Lam) <- G(lam, Lam)
+template <int N>
+__device__ void apply_adj(const Map<N>& a, double (&lam)[N], double (&Lam)[N][N]) {
+  double t[N], LP[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = fma(a.P[j][i], lam[j], s);
+    t[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double q = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) q = fma(Lam[i][k], a.P[k][j], q);
+      LP[i][j] = q;
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    lam[i] = t[i] + a.w[i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double q = 0.5 * (a.C[i][j] + a.C[j][i]) + 0.5 * (t[i] * a.w[j] + t[j] * a.w[i]);
+#pragma unroll
+      for (int k = 0; k < N; ++k) q = fma(a.P[k][i], LP[k][j], q);
+      Lam[i][j] = q;
+      Lam[j][i] = q;
+    }
+  }
+}
+template <int N, bool ADJ>
+__device__ __forceinline__ void compose_sel(const Map<N>& a, const Map<N>& b, Map<N>& out) {
+  if constexpr (ADJ) compose_adj<N>(a, b, out); else compose<N>(a, b, out);
+}
+template <int N, bool ADJ>
+__device__ __forceinline__ void apply_sel(const Map<N>& a, double (&x)[N], double (&X)[N][N]) {
+  if constexpr (ADJ) apply_adj<N>(a, x, X); else apply<N>(a, x, X);
+}
+
+// ------------------------------------------------------------------------------------------------
 // small dense helpers (row-major, compile-time shapes)
 // ------------------------------------------------------------------------------------------------
 template <int R, int C>
@@ -648,7 +732,7 @@ k_selem(ModelPtrs mp, const double* __restrict__ fm, const double* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Scan order: REV = false walks the steps forwards; REV = true backwards (the smoother), chunk c has scan position
 // Cn - 1 - c and its steps compose from the last to the first.
-template <int N, bool REV>
+template <int N, bool REV, bool ADJ = false>
 __global__ void __launch_bounds__(kElemBlock)
 k_reduce(const double* __restrict__ rec, Lay lay, double* __restrict__ items) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,7 +744,7 @@ k_reduce(const double* __restrict__ rec, Lay lay, double* __restrict__ items) {
   for (int jj = 0; jj < lay.K; ++jj) {
     const int j = REV ? lay.K - 1 - jj : jj;
     e.load(rec + (long long)j * lay.Cn + c, fs);
-    compose<N>(acc, e, o);
+    compose_sel<N, ADJ>(acc, e, o);
     acc = o;
   }
   const long long pos = REV ? lay.Cn - 1 - c : c;
@@ -670,7 +754,7 @@ k_reduce(const double* __restrict__ rec, Lay lay, double* __restrict__ items) {
 // Inclusive Hillis-Steele scan of the `count` maps of one CTA's segment (ping-pong between bufA and bufB, both
 // [NT][stride]); writes the EXCLUSIVE prefix of every item to pref [NT][stride] and the segment total to
 // tot [NT][gridDim.x].
-template <int N>
+template <int N, bool ADJ = false>
 __global__ void __launch_bounds__(kScanBlock)
 k_bscan(double* __restrict__ bufA, double* __restrict__ bufB, long long count, long long stride,
         double* __restrict__ pref, double* __restrict__ tot) {
@@ -685,7 +769,7 @@ k_bscan(double* __restrict__ bufA, double* __restrict__ bufB, long long count, l
       b.load(cur + i, stride);
       if ((int)threadIdx.x >= d) {
         a.load(cur + i - d, stride);
-        compose<N>(a, b, o);
+        compose_sel<N, ADJ>(a, b, o);
         o.store(nxt + i, stride);
       } else {
         b.store(nxt + i, stride);
@@ -705,7 +789,7 @@ k_bscan(double* __restrict__ bufA, double* __restrict__ bufB, long long count, l
   }
 }
 
-template <int N, bool REV>
+template <int N, bool REV, bool ADJ = false>
 __global__ void __launch_bounds__(kElemBlock)
 k_apply(const double* __restrict__ rec, const double* __restrict__ recB, Lay lay, const double* __restrict__ pref,
         const double* __restrict__ bpref, long long nblk, const double* __restrict__ dm0,
@@ -724,9 +808,9 @@ k_apply(const double* __restrict__ rec, const double* __restrict__ recB, Lay lay
     for (int q = 0; q < i; ++q) { const double v = 0.5 * (dP[i][q] + dP[q][i]); dP[i][q] = v; dP[q][i] = v; }
   Map<N> e;
   e.load(bpref + pos / kScanBlock, nblk);
-  apply<N>(e, dm, dP);
+  apply_sel<N, ADJ>(e, dm, dP);
   e.load(pref + pos, lay.Cn);
-  apply<N>(e, dm, dP);
+  apply_sel<N, ADJ>(e, dm, dP);
   double dell = 0.0;
 #pragma unroll 1
   for (int jj = 0; jj < lay.K; ++jj) {
@@ -747,7 +831,7 @@ k_apply(const double* __restrict__ rec, const double* __restrict__ recB, Lay lay
       dell += v;
     }
     e.load(rec + (long long)j * lay.Cn + c, fs);
-    apply<N>(e, dm, dP);
+    apply_sel<N, ADJ>(e, dm, dP);
     const long long o = REV ? k : k + 1;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -757,6 +841,196 @@ k_apply(const double* __restrict__ rec, const double* __restrict__ recB, Lay lay
     }
   }
   if (!REV && dell_part) dell_part[c] = dell;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse mode: records of the adjoint scan from the forward records, and the per-step gradient contraction
+// ------------------------------------------------------------------------------------------------
+// recA (Map layout: Phi, w, 0, B) from rec (Phi, w, ., .) and recB (B packed with doubled off-diagonals, e)
+template <int N>
+__global__ void __launch_bounds__(kElemBlock)
+k_adj_prep(const double* rec, const double* __restrict__ recB, Lay lay, double* recA) {   // rec may alias recA
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lay.Cn * lay.K) return;
+  const long long fs = (long long)lay.K * lay.Cn;
+  Map<N> e;
+  e.load(rec + t, fs);
+  int f = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    e.c[i] = 0.0;
+#pragma unroll
+    for (int q = 0; q <= i; ++q) {
+      const double v = recB[t + (long long)(f++) * fs];
+      e.C[i][q] = (i == q) ? v : 0.5 * v;
+      e.C[q][i] = e.C[i][q];
+    }
+  }
+  e.store(recA + t, fs);
+}
+
+// d ell / d (F, Q, b, H, R, c)_k from the costates (lam, Lam)_{k+1} and the primal step (covariance form for Q, R):
+//   u = Phiu^T lam', kl = K^T lam', h = H^T s
+//   gb = u + h                     gQ = Phiu^T Lam' Phiu + sym(u h^T) + (h h^T - H^T S^-1 H) / 2
+//   gF = gb m^T + 2 gQ F P         gc = s - kl
+//   gR = K^T Lam' K - sym(kl s^T) + (s s^T - S^-1) / 2
+//   gH = -2 K^T Lam' Phiu Pp + s (Pp u + mp + Pp h)^T - kl (mp + Pp h)^T - S^-1 H Pp
+template <int N, int NY>
+__global__ void __launch_bounds__(kElemBlock)
+k_adj_grad(ModelPtrs mp, const double* __restrict__ y, const double* __restrict__ fm, const double* __restrict__ fL,
+           const double* __restrict__ lam, const double* __restrict__ Lam, long long T, double* __restrict__ gF,
+           double* __restrict__ gQ, double* __restrict__ gb, double* __restrict__ gH, double* __restrict__ gR,
+           double* __restrict__ gc) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= T) return;
+  double m[N], L[N][N], F[N][N], cQ[N][N], b[N], H[NY][N], cR[NY][NY], c[NY], yk[NY], l1[N], L1[N][N];
+  load_vec<N>(fm + k * N, m);
+  load_mat<N, N>(fL + k * N * N, L);
+  load_mat<N, N>(mp.F + k * mp.F_ts, F);
+  load_mat<N, N>(mp.cholQ + k * mp.cholQ_ts, cQ);
+  zero_upper<N>(cQ);
+  load_vec<N>(mp.b + k * mp.b_ts, b);
+  load_mat<NY, N>(mp.H + k * mp.H_ts, H);
+  load_mat<NY, NY>(mp.cholR + k * mp.cholR_ts, cR);
+  load_vec<NY>(mp.c + k * mp.c_ts, c);
+  load_vec<NY>(y + k * NY, yk);
+  load_vec<N>(lam + (k + 1) * N, l1);
+  load_mat<N, N>(Lam + (k + 1) * N * N, L1);
+  double P[N][N], Q[N][N], R[NY][NY];
+  mmt<N, N, N>(L, L, P);
+  mmt<N, N, N>(cQ, cQ, Q);
+  mmt<NY, NY, NY>(cR, cR, R);
+  double mpred[N], FP[N][N], Pp[N][N];
+  mv<N, N>(F, m, mpred);
+#pragma unroll
+  for (int i = 0; i < N; ++i) mpred[i] += b[i];
+  mm<N, N, N>(F, P, FP);
+  mmt<N, N, N>(FP, F, Pp);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int q = 0; q < N; ++q) Pp[i][q] += Q[i][q];
+  double HPp[NY][N], S[NY][NY], Ls[NY][NY];
+  mm<NY, N, N>(H, Pp, HPp);
+  mmt<NY, N, NY>(HPp, H, S);
+#pragma unroll
+  for (int i = 0; i < NY; ++i)
+#pragma unroll
+    for (int q = 0; q < NY; ++q) S[i][q] += R[i][q];
+#pragma unroll
+  for (int i = 0; i < NY; ++i)
+#pragma unroll
+    for (int q = 0; q < NY; ++q) Ls[i][q] = 0.5 * (S[i][q] + S[q][i]);
+  chol_lower<NY>(Ls);
+  double s1[NY][1], sv[NY];
+  {
+    double r[NY];
+    mv<NY, N>(H, mpred, r);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) s1[i][0] = yk[i] - r[i] - c[i];
+    cho_solve<NY, 1>(Ls, s1);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) sv[i] = s1[i][0];
+  }
+  double Kt[NY][N];
+#pragma unroll
+  for (int i = 0; i < NY; ++i)
+#pragma unroll
+    for (int q = 0; q < N; ++q) Kt[i][q] = HPp[i][q];
+  cho_solve<NY, N>(Ls, Kt);   // K^T = S^-1 H Pp
+  double Phiu[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double v = (i == q) ? 1.0 : 0.0;
+#pragma unroll
+      for (int a = 0; a < NY; ++a) v = fma(-Kt[a][i], H[a][q], v);
+      Phiu[i][q] = v;
+    }
+  double h[N], u[N], kl[NY];
+  mtv<NY, N>(H, sv, h);
+  mtv<N, N>(Phiu, l1, u);
+  mv<NY, N>(Kt, l1, kl);
+  double Si[NY][NY];   // S^-1
+#pragma unroll
+  for (int i = 0; i < NY; ++i)
+#pragma unroll
+    for (int q = 0; q < NY; ++q) Si[i][q] = (i == q) ? 1.0 : 0.0;
+  cho_solve<NY, NY>(Ls, Si);
+  // gQ
+  double GA[N][N];
+  {
+    double T1[N][N], SiH[NY][N];
+    mm<N, N, N>(L1, Phiu, T1);            // Lam' Phiu
+    mm<NY, NY, N>(Si, H, SiH);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double v = 0.5 * (u[i] * h[q] + u[q] * h[i]) + 0.5 * h[i] * h[q];
+#pragma unroll
+        for (int a = 0; a < N; ++a) v = fma(Phiu[a][i], T1[a][q], v);
+#pragma unroll
+        for (int a = 0; a < NY; ++a) v = fma(-0.5 * H[a][i], SiH[a][q], v);
+        GA[i][q] = v;
+      }
+  }
+  double ga[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    ga[i] = u[i] + h[i];
+    gb[k * N + i] = ga[i];
+  }
+  {
+    double GAs[N][N], G2[N][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        GAs[i][q] = 0.5 * (GA[i][q] + GA[q][i]);
+        gQ[(k * N + i) * N + q] = GAs[i][q];
+      }
+    mm<N, N, N>(GAs, FP, G2);             // gQ F P
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int q = 0; q < N; ++q) gF[(k * N + i) * N + q] = fma(ga[i], m[q], 2.0 * G2[i][q]);
+  }
+  // gc, gR
+#pragma unroll
+  for (int a = 0; a < NY; ++a) gc[k * NY + a] = sv[a] - kl[a];
+  double KtL[NY][N];                       // K^T Lam'
+  mm<NY, N, N>(Kt, L1, KtL);
+#pragma unroll
+  for (int a = 0; a < NY; ++a)
+#pragma unroll
+    for (int q = 0; q < NY; ++q) {
+      double v = -0.5 * (kl[a] * sv[q] + kl[q] * sv[a]) + 0.5 * (sv[a] * sv[q] - 0.5 * (Si[a][q] + Si[q][a]));
+#pragma unroll
+      for (int i = 0; i < N; ++i) v = fma(0.5 * KtL[a][i], Kt[q][i], v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) v = fma(0.5 * KtL[q][i], Kt[a][i], v);
+      gR[(k * NY + a) * NY + q] = v;
+    }
+  // gH
+  {
+    double Ppu[N], Pph[N], W[N][N], KLW[NY][N], SiHPp[NY][N];
+    mv<N, N>(Pp, u, Ppu);
+    mv<N, N>(Pp, h, Pph);
+    mm<N, N, N>(Phiu, Pp, W);              // Phiu Pp
+    mm<NY, N, N>(KtL, W, KLW);             // K^T Lam' Phiu Pp
+#pragma unroll
+    for (int a = 0; a < NY; ++a)
+#pragma unroll
+      for (int q = 0; q < N; ++q) SiHPp[a][q] = Kt[a][q];   // S^-1 H Pp = K^T
+#pragma unroll
+    for (int a = 0; a < NY; ++a)
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        gH[(k * NY + a) * N + q] = -2.0 * KLW[a][q] + sv[a] * (Ppu[q] + mpred[q] + Pph[q]) -
+                                   kl[a] * (mpred[q] + Pph[q]) - SiHPp[a][q];
+  }
 }
 
 // fixed-order sum of n partials (one CTA)
@@ -874,15 +1148,15 @@ struct Bufs {
   }
 };
 
-template <int N, bool REV>
+template <int N, bool REV, bool ADJ = false>
 void run_scan(const Bufs<N>& B, const Lay& l, const double* dm0, const double* dP0, double* dm_out, double* dP_out,
               bool ell, cudaStream_t st) {
   const unsigned cb = (unsigned)ceil_div(l.Cn, kElemBlock);
   const long long nblk = ceil_div(l.Cn, kScanBlock);
-  k_reduce<N, REV><<<cb, kElemBlock, 0, st>>>(B.rec, l, B.items);
-  k_bscan<N><<<(unsigned)nblk, kScanBlock, 0, st>>>(B.items, B.pp, l.Cn, l.Cn, B.pref, B.btot);
-  k_bscan<N><<<1, kScanBlock, 0, st>>>(B.btot, B.bpp, nblk, nblk, B.bpref, B.gtot);
-  k_apply<N, REV><<<cb, kElemBlock, 0, st>>>(B.rec, ell ? B.recB : nullptr, l, B.pref, B.bpref, nblk, dm0, dP0, dm_out,
+  k_reduce<N, REV, ADJ><<<cb, kElemBlock, 0, st>>>(B.rec, l, B.items);
+  k_bscan<N, ADJ><<<(unsigned)nblk, kScanBlock, 0, st>>>(B.items, B.pp, l.Cn, l.Cn, B.pref, B.btot);
+  k_bscan<N, ADJ><<<1, kScanBlock, 0, st>>>(B.btot, B.bpp, nblk, nblk, B.bpref, B.gtot);
+  k_apply<N, REV, ADJ><<<cb, kElemBlock, 0, st>>>(B.rec, ell ? B.recB : nullptr, l, B.pref, B.bpref, nblk, dm0, dP0, dm_out,
                                              dP_out, ell ? B.dellp : nullptr);
 }
 
@@ -904,6 +1178,37 @@ int run_pass(const ModelPtrs& mp, const double* y, long long T, const double* fm
     run_scan<N, true>(B, l, dfm + T * N, dfP + T * N * N, dsm, dsP, false, st);
   }
   return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA;
+}
+
+template <int N, int NY>
+int run_adjoint(const ModelPtrs& mp, const double* y, long long T, const double* fm, const double* fL, double* lam,
+                double* Lam, double* gF, double* gQ, double* gb, double* gH, double* gR, double* gc, double* ws,
+                cudaStream_t st) {
+  const Lay l = make_lay(T);
+  Bufs<N> B(ws, l);
+  const unsigned eb = (unsigned)ceil_div(l.Cn * l.K, kElemBlock);
+  // forward records with zero model tangents: (Phi, w) and (B, .) of every step
+  k_felem<N, NY><<<eb, kElemBlock, 0, st>>>(mp, y, fm, fL, l, B.rec, B.recB);
+  // adjoint records overwrite the forward ones (each thread reads its own record before it writes it)
+  k_adj_prep<N><<<eb, kElemBlock, 0, st>>>(B.rec, B.recB, l, B.rec);
+  k_copy_state<N><<<1, N * N < 32 ? 32 : N * N, 0, st>>>(nullptr, nullptr, 0, lam, Lam, T);
+  run_scan<N, true, true>(B, l, nullptr, nullptr, lam, Lam, false, st);
+  k_adj_grad<N, NY><<<(unsigned)ceil_div(T, kElemBlock), kElemBlock, 0, st>>>(mp, y, fm, fL, lam, Lam, T, gF, gQ, gb, gH,
+                                                                               gR, gc);
+  return cudaGetLastError() == cudaSuccess ? PSQRT_OK : PSQRT_ECUDA;
+}
+
+template <int N>
+int dispatch_adjoint(int ny, const ModelPtrs& mp, const double* y, long long T, const double* fm, const double* fL,
+                     double* lam, double* Lam, double* gF, double* gQ, double* gb, double* gH, double* gR, double* gc,
+                     double* ws, cudaStream_t st) {
+  switch (ny) {
+    case 1: return run_adjoint<N, 1>(mp, y, T, fm, fL, lam, Lam, gF, gQ, gb, gH, gR, gc, ws, st);
+    case 2: return run_adjoint<N, 2>(mp, y, T, fm, fL, lam, Lam, gF, gQ, gb, gH, gR, gc, ws, st);
+    case 3: return run_adjoint<N, 3>(mp, y, T, fm, fL, lam, Lam, gF, gQ, gb, gH, gR, gc, ws, st);
+    case 4: return run_adjoint<N, 4>(mp, y, T, fm, fL, lam, Lam, gF, gQ, gb, gH, gR, gc, ws, st);
+    default: return PSQRT_EUNSUPPORTED;
+  }
 }
 
 template <int N>
@@ -1237,6 +1542,38 @@ int psqrt_filter_smoother_tangent(const psqrt_ssm* ssm, const psqrt_ssm_tangent*
     default: return PSQRT_EUNSUPPORTED;
   }
 #undef PSQ_TNX
+}
+
+int psqrt_loglik_adjoint(const psqrt_ssm* ssm, const double* y, int nx, int ny, int64_t T, const double* fm,
+                         const double* fL, double* lam, double* Lam, double* gF, double* gQ, double* gb, double* gH,
+                         double* gR, double* gc, void* ws, size_t ws_bytes, void* stream) {
+  if (!ssm || !y || !fm || !fL || !lam || !Lam || !gF || !gQ || !gb || !gH || !gR || !gc || !ws || T <= 0)
+    return PSQRT_EINVAL;
+  if (!ssm->F || !ssm->cholQ || !ssm->b || !ssm->H || !ssm->cholR || !ssm->c) return PSQRT_EINVAL;
+  const size_t need = psqrt_tangent_workspace_bytes(nx, ny, T);
+  if (need == 0) return PSQRT_EUNSUPPORTED;
+  if (ws_bytes < need) return PSQRT_EWORKSPACE;
+  ModelPtrs mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.F = ssm->F; mp.cholQ = ssm->cholQ; mp.b = ssm->b; mp.H = ssm->H; mp.cholR = ssm->cholR; mp.c = ssm->c;
+  mp.F_ts = ssm->F_ts; mp.cholQ_ts = ssm->cholQ_ts; mp.b_ts = ssm->b_ts;
+  mp.H_ts = ssm->H_ts; mp.cholR_ts = ssm->cholR_ts; mp.c_ts = ssm->c_ts;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* w = (double*)ws;
+#define PSQ_ANX(NV)                                                                                                \
+  case NV:                                                                                                         \
+    return dispatch_adjoint<NV>(ny, mp, y, T, fm, fL, lam, Lam, gF, gQ, gb, gH, gR, gc, w, st)
+  switch (nx) {
+    PSQ_ANX(1);
+    PSQ_ANX(2);
+    PSQ_ANX(3);
+    PSQ_ANX(4);
+    PSQ_ANX(5);
+    PSQ_ANX(6);
+    PSQ_ANX(8);
+    default: return PSQRT_EUNSUPPORTED;
+  }
+#undef PSQ_ANX
 }
 
 int psqrt_cov_tangent_to_chol(const double* L, const double* dP, double* dL, int n, int64_t count, void* stream) {

@@ -61,7 +61,8 @@ EXPORTS = (
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
     "psqrt_smoother_combine", "psqrt_tria_batched", "psqrt_chol_update_batched", "psqrt_linearize_builtin",
     "psqrt_fp64_probe", "psqrt_peer_layout", "psqrt_sampler_workspace_bytes", "psqrt_sample_paths",
-    "psqrt_tangent_workspace_bytes", "psqrt_filter_smoother_tangent", "psqrt_cov_tangent_to_chol",
+    "psqrt_tangent_workspace_bytes", "psqrt_filter_smoother_tangent", "psqrt_loglik_adjoint",
+    "psqrt_cov_tangent_to_chol",
     "psqrt_linearize_builtin_tangent", "psqrt_count_nonfinite", "psqrt_supported_generic",
     "psqrt_generic_workspace_bytes", "psqrt_filter_smoother_generic", "psqrt_filter_smoother_f32", "psqrt_tria_generic",
     "psqrt_chol_update_generic",
@@ -740,6 +741,34 @@ def filter_smoother_tangent(ssm: LinearizedSSM, dssm: dict, y: torch.Tensor, fm,
                                                ctypes.c_size_t(ws.numel()), _stream())
     _check(rc, "psqrt_filter_smoother_tangent")
     return dfm, dfP, dsm, dsP, (dell[0] if loglik else None)
+
+
+def loglik_adjoint(ssm: LinearizedSSM, y: torch.Tensor, fm: torch.Tensor, fL: torch.Tensor) -> dict:
+    """psqrt_loglik_adjoint for one sequence: reverse mode of the log-likelihood at the linearised model `ssm`.
+    (fm, fL): the filtered trajectory of filter_smoother on the same inputs.  Returns
+    {"lam" [T+1,nx], "Lam" [T+1,nx,nx], "gF" [T,nx,nx], "gQ" [T,nx,nx], "gb" [T,nx], "gH" [T,ny,nx], "gR" [T,ny,ny],
+    "gc" [T,ny]}: d ell / d (filtered mean, filtered covariance) of every step (index 0: the prior) and d ell / d (model
+    entries of every step), Q and R in COVARIANCE form."""
+    lib = load()
+    T, ny = y.shape
+    nx = fm.shape[-1]
+    dev = y.device
+    keep = []
+    s = ssm.struct(T, 1, keep)
+    nbytes = int(lib.psqrt_tangent_workspace_bytes(nx, ny, ctypes.c_int64(T)))
+    if nbytes == 0:
+        raise PsqrtError(f"psqrt_loglik_adjoint: unsupported nx={nx}, ny={ny}")
+    ws = workspace(nbytes, dev, slot=-1)
+    new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+    out = {"lam": new(T + 1, nx), "Lam": new(T + 1, nx, nx), "gF": new(T, nx, nx), "gQ": new(T, nx, nx),
+           "gb": new(T, nx), "gH": new(T, ny, nx), "gR": new(T, ny, ny), "gc": new(T, ny)}
+    yc, fmc, fLc = y.contiguous(), fm.contiguous(), fL.contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.psqrt_loglik_adjoint(ctypes.byref(s), _ptr(yc), nx, ny, ctypes.c_int64(T), _ptr(fmc), _ptr(fLc),
+                                      *[_ptr(out[k]) for k in ("lam", "Lam", "gF", "gQ", "gb", "gH", "gR", "gc")],
+                                      ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()), _stream())
+    _check(rc, "psqrt_loglik_adjoint")
+    return out
 
 
 def cov_tangent_to_chol(L: torch.Tensor, dP: torch.Tensor) -> torch.Tensor:

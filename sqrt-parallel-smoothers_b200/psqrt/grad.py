@@ -29,7 +29,8 @@ import torch
 from . import _lib, methods
 from ._base import ConditionalMomentsModel, FunctionalModel, MVNSqrt
 
-__all__ = ["Tangents", "TangentPass", "loglikelihood_jvp", "value_and_grad"]
+__all__ = ["Tangents", "TangentPass", "loglikelihood_jvp", "value_and_grad", "Cotangents", "loglikelihood_vjp",
+           "value_and_grad_reverse"]
 
 
 class Tangents(NamedTuple):
@@ -274,3 +275,91 @@ def value_and_grad(build: Callable, theta, observations, linearization_method: C
                                          True, criterion, implicit_terms)
         grad[i] = dell
     return ell, grad
+
+
+# ---- reverse mode: d ell / d (everything) at a fixed linearised model in ONE adjoint pass --------------------------
+class Cotangents(NamedTuple):
+    """Gradient of the log-likelihood of one filtering pass with respect to its inputs (what ``jax.grad`` returns for
+    the same arguments of ``parsmooth.methods.filtering(..., return_loglikelihood=True)`` at a FIXED nominal
+    trajectory).  `x0`, `transition_noise`, `observation_noise`: MVNSqrt of gradients w.r.t. (mean, chol) -- factors,
+    like differentiating the reference's inputs (noise entries None for a ConditionalMomentsModel).  `model`: the
+    per-step gradients {"gF","gQ","gb","gH","gR","gc"} w.r.t. the linearised model (Q, R in covariance form) and the
+    costates {"lam","Lam"} = d ell / d (filtered mean, covariance) of every step."""
+    x0: MVNSqrt
+    transition_noise: Optional[MVNSqrt]
+    observation_noise: Optional[MVNSqrt]
+    model: dict
+
+
+def loglikelihood_vjp(observations, x0, transition_model, observation_model, linearization_method: Callable,
+                      nominal_trajectory: Optional[MVNSqrt] = None, parallel: bool = True):
+    """(filtered, ell, Cotangents): ``filtering(..., return_loglikelihood=True)`` (methods.py:14-24) and the gradient
+    of ell w.r.t. the prior, the additive noises and every entry of the linearised model of every step, by ONE adjoint
+    pass (psqrt_loglik_adjoint: the costate recursion of the Kalman filter as a reverse associative scan).  The cost
+    does not depend on the number of parameters; for a linear-Gaussian model (psqrt.models.lgssm) this is the complete
+    gradient.  For a nonlinear model it is the derivative at a fixed nominal trajectory -- the term ``d ell/d theta``
+    of the module docstring; the dependence through the nominal trajectory stays in forward mode
+    (loglikelihood_jvp)."""
+    methods._check_parallel(parallel)
+    dev = methods._device()
+    ys = methods._t(observations, dev)
+    x0 = methods._mvn(x0, dev)
+    tm = methods._model(transition_model, dev)
+    om = methods._model(observation_model, dev)
+    T = ys.shape[0]
+    if nominal_trajectory is None:
+        nominal_trajectory = methods._default_nominal(T + 1, x0.mean.shape[-1], dev)
+    nominal = methods._mvn(nominal_trajectory, dev)
+    ssm = methods._linearize(linearization_method, tm, om, nominal)
+    L0 = methods._prior_factor(x0.chol)
+    fm, fL, _, _, ell = _lib.filter_smoother(ssm, ys, x0.mean, L0, smooth=False, loglik=True)
+    g = _lib.loglik_adjoint(ssm, ys, fm, fL)
+
+    def noise(model, gm, gcov):
+        if not isinstance(model, FunctionalModel):
+            return None
+        chol = model.mvn.chol
+        S = gcov.sum(0)
+        return MVNSqrt(gm.sum(0), (S + S.transpose(-1, -2)) @ chol)
+
+    Lam0 = g["Lam"][0]
+    gx0 = MVNSqrt(g["lam"][0], (Lam0 + Lam0.transpose(-1, -2)) @ x0.chol)
+    return MVNSqrt(fm, fL), ell, Cotangents(gx0, noise(tm, g["gb"], g["gQ"]), noise(om, g["gc"], g["gR"]), g)
+
+
+def value_and_grad_reverse(build: Callable, theta, observations, linearization_method: Callable,
+                           nominal_trajectory: Optional[MVNSqrt] = None):
+    """(ell, d ell / d theta) for ``build(theta) -> (x0, transition_model, observation_model)`` at a fixed nominal
+    trajectory, ALL components of theta from one adjoint pass: the cotangents of loglikelihood_vjp are pulled back
+    through `build` with torch.autograd (means / factors of x0 and of the two noises must be torch functions of
+    theta; the model functions themselves may not depend on it).  The analogue of
+    ``jax.value_and_grad(lambda theta: filtering(ys, *build(theta), lin, nominal, True, True)[1])``."""
+    dev = methods._device()
+    theta = torch.as_tensor(theta, dtype=torch.float64).reshape(-1).to(dev).detach().requires_grad_(True)
+    with torch.enable_grad():
+        x0, tm, om = build(theta)
+        leaves = [x0.mean, x0.chol]
+        for m in (tm, om):
+            if isinstance(m, FunctionalModel):
+                leaves += [m.mvn.mean, m.mvn.chol]
+        leaves = [torch.as_tensor(v, dtype=torch.float64).to(dev) for v in leaves]
+    det = [v.detach() for v in leaves]
+    k = 2
+    tm_d, om_d = tm, om
+    if isinstance(tm, FunctionalModel):
+        tm_d = FunctionalModel(tm.function, MVNSqrt(det[k], det[k + 1]))
+        k += 2
+    if isinstance(om, FunctionalModel):
+        om_d = FunctionalModel(om.function, MVNSqrt(det[k], det[k + 1]))
+    _, ell, ct = loglikelihood_vjp(observations, MVNSqrt(det[0], det[1]), tm_d, om_d, linearization_method,
+                                   nominal_trajectory)
+    cots = [ct.x0.mean, ct.x0.chol]
+    for c in (ct.transition_noise, ct.observation_noise):
+        if c is not None:
+            cots += [c.mean, c.chol]
+    pairs = [(v, c) for v, c in zip(leaves, cots) if v.requires_grad]
+    if not pairs:
+        return ell, torch.zeros_like(theta)
+    (grad,) = torch.autograd.grad([v for v, _ in pairs], [theta], [c.reshape(v.shape) for v, c in pairs],
+                                  allow_unused=True)
+    return ell, (torch.zeros_like(theta) if grad is None else grad).detach()

@@ -71,3 +71,57 @@ def compose(a, b):
 def apply(a, dm, dP):
     P, w, c, C = a
     return P @ (dm + dP @ w) + c, P @ dP @ P.T + C
+
+
+# ---- reverse mode (psqrt_loglik_adjoint): compose_adj / apply_adj / k_adj_grad, formula for formula ------------------
+def adj_map(felem_map, rec):
+    """forward step record -> adjoint map (Psi, v, D):  lam = Psi^T lam' + v,  Lam = Psi^T Lam' Psi + sym((Psi^T lam') v^T) + D"""
+    Phi, w, _, _ = felem_map
+    B, _ = rec
+    return Phi, w, 0.5 * (B + B.T)
+
+
+def compose_adj(a, b):
+    """G_b o G_a: a = the LATER steps (applied first going backwards), b = the earlier ones"""
+    Pa, wa, Da = a
+    Pb, wb, Db = b
+    t = Pb.T @ wa
+    return Pa @ Pb, wb + t, Db + 0.5 * (np.outer(t, wb) + np.outer(wb, t)) + Pb.T @ Da @ Pb
+
+
+def apply_adj(a, lam, Lam):
+    P, w, D = a
+    t = P.T @ lam
+    return t + w, P.T @ Lam @ P + 0.5 * (np.outer(t, w) + np.outer(w, t)) + D
+
+
+def adj_grad(F, cQ, b, H, cR, c, y, m, L, l1, L1):
+    """d ell / d (F, Q, b, H, R, c) of one step from the costates (l1, L1) of the NEXT filtered state (k_adj_grad);
+    Q, R in covariance form."""
+    n = F.shape[0]
+    P = L @ L.T
+    cQ = np.tril(cQ)
+    Q, R = cQ @ cQ.T, cR @ cR.T
+    mp = F @ m + b
+    FP = F @ P
+    Pp = FP @ F.T + Q
+    HPp = H @ Pp
+    S = HPp @ H.T + R
+    S = 0.5 * (S + S.T)
+    s = np.linalg.solve(S, y - H @ mp - c)
+    Kt = np.linalg.solve(S, HPp)
+    Phiu = np.eye(n) - Kt.T @ H
+    h = H.T @ s
+    u = Phiu.T @ l1
+    kl = Kt @ l1
+    Si = np.linalg.inv(S)
+    sym = lambda X: 0.5 * (X + X.T)
+    GA = Phiu.T @ L1 @ Phiu + sym(np.outer(u, h)) + 0.5 * np.outer(h, h) - 0.5 * H.T @ Si @ H
+    gQ = sym(GA)
+    gb = u + h
+    gF = np.outer(gb, m) + 2.0 * gQ @ FP
+    gc = s - kl
+    KtL = Kt @ L1
+    gR = sym(KtL @ Kt.T) - sym(np.outer(kl, s)) + 0.5 * (np.outer(s, s) - sym(Si))
+    gH = -2.0 * KtL @ Phiu @ Pp + np.outer(s, Pp @ u + mp + Pp @ h) - np.outer(kl, mp + Pp @ h) - Kt
+    return gF, gQ, gb, gH, gR, gc

@@ -239,3 +239,102 @@ def test_loglikelihood_gradient_lgssm_all_parameters():
     assert abs(tp.ell.item() - oracle_ell(0.0)) < 1e-8 * abs(tp.ell.item())
     dell = tp.ell_jvp(None)
     assert abs(dell.item() - ref) < 1e-6 * max(1.0, abs(ref)), (dell.item(), ref)
+
+
+@pytest.mark.parametrize("n,ny,T", [(4, 2, 300), (5, 2, 1000), (1, 1, 40), (2, 1, 7), (3, 3, 257), (6, 4, 90),
+                                    (8, 4, 70), (4, 2, 1), (5, 2, 9000), (4, 2, 70000)])
+def test_adjoint_pass(n, ny, T):
+    """psqrt_loglik_adjoint (reverse mode) on a time-varying model:
+      * the dot-product test against the forward-mode tangent pass for a random direction of every model entry and of
+        the prior (<gradient, direction> == d ell) -- 1e-9,
+      * costates and per-step gradients against the NumPy mirror of the adjoint algebra (tests/_tangent_maps.py, itself
+        checked against the oracle's direct differentiation on the CPU) on short cases -- 1e-9."""
+    from psqrt import _lib
+    import _tangent_maps as TM
+    case = time_varying_case(n, ny, T, seed=5 * n + ny)
+    rng = np.random.RandomState(n + T + 1)
+    d = dict(dF=0.3 * rng.randn(T, n, n), dcQ=np.tril(rng.randn(T, n, n)) * 0.1, db=rng.randn(T, n),
+             dH=rng.randn(T, ny, n), dcR=0.1 * rng.randn(T, ny, ny), dc=rng.randn(T, ny))
+    dm0, dL0 = rng.randn(n), np.tril(rng.randn(n, n))
+    dQ, dR, dP0 = _sym(d["dcQ"], case["cholQ"]), _sym(d["dcR"], case["cholR"]), _sym(dL0, case["L0"])
+    ssm = _lib.LinearizedSSM(*[_g(case[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c")])
+    ys = _g(case["ys"])
+    fm, fL, _, _, _ = _lib.filter_smoother(ssm, ys, _g(case["m0"]), _g(case["L0"]), smooth=False, loglik=True)
+    g = _lib.loglik_adjoint(ssm, ys, fm, fL)
+    dssm = {"dF": _g(d["dF"]), "dQ": _g(dQ), "db": _g(d["db"]), "dH": _g(d["dH"]), "dR": _g(dR), "dc": _g(d["dc"])}
+    _, _, _, _, dell = _lib.filter_smoother_tangent(ssm, dssm, ys, fm, fL, None, None, _g(dm0), _g(dP0), smooth=False)
+    dot = (g["lam"][0] @ _g(dm0) + (g["Lam"][0] * _g(dP0)).sum() + (g["gF"] * dssm["dF"]).sum() +
+           (g["gQ"] * dssm["dQ"]).sum() + (g["gb"] * dssm["db"]).sum() + (g["gH"] * dssm["dH"]).sum() +
+           (g["gR"] * dssm["dR"]).sum() + (g["gc"] * dssm["dc"]).sum())
+    scale = sum(float((g[k] * dssm["d" + k[1:]]).abs().sum()) for k in ("gF", "gQ", "gb", "gH", "gR", "gc"))
+    assert abs(dot.item() - dell.item()) < 1e-9 * max(1.0, scale), (dot.item(), dell.item())
+    assert float(g["lam"][T].abs().max()) == 0.0 and float(g["Lam"][T].abs().max()) == 0.0
+    assert float((g["Lam"] - g["Lam"].transpose(-1, -2)).abs().max()) < 1e-12 * max(1.0, float(g["Lam"].abs().max()))
+    if T > 2000:
+        return
+    fmn, fLn = fm.cpu().numpy(), fL.cpu().numpy()
+    lam = np.zeros((T + 1, n))
+    Lam = np.zeros((T + 1, n, n))
+    z = np.zeros
+    ref = {k: [] for k in ("gF", "gQ", "gb", "gH", "gR", "gc")}
+    for t in range(T - 1, -1, -1):
+        args = [case[k][t] for k in ("F", "cholQ", "b", "H", "cholR", "c")] + [case["ys"][t], fmn[t], fLn[t]]
+        a, r = TM.felem(*args, z((n, n)), z((n, n)), z(n), z((ny, n)), z((ny, ny)), z(ny))
+        for k, v in zip(("gF", "gQ", "gb", "gH", "gR", "gc"), TM.adj_grad(*args, lam[t + 1], Lam[t + 1])):
+            ref[k].append(v)
+        lam[t], Lam[t] = TM.apply_adj(TM.adj_map(a, r), lam[t + 1], Lam[t + 1])
+    assert rel_err(g["lam"].cpu().numpy(), lam) < 1e-9
+    assert rel_err(g["Lam"].cpu().numpy(), Lam) < 1e-9
+    for k in ref:
+        assert rel_err(g[k].cpu().numpy(), np.stack(ref[k][::-1])) < 1e-9, k
+
+
+def test_reverse_mode_lgssm_gradient_vs_oracle_differences():
+    """psqrt.grad.value_and_grad_reverse: all parameters of an LGSSM from ONE adjoint pass, against central differences
+    of the oracle's parallel filter log-likelihood (reference-pinned) and against the forward-mode path."""
+    import psqrt
+    from psqrt import grad as G
+    from psqrt.models import lgssm
+    n, ny, T = 4, 2, 400
+    case = lgssm_case(n, ny, T, seed=9)
+    ys = _g(case["ys"])
+    base = {k: _g(case[k]) for k in ("m0", "L0", "b", "cholQ", "c", "cholR")}
+    theta0 = np.array([0.3, -0.2, 0.15, 0.4, -0.1, 0.25, 0.05])
+
+    def build(th):
+        x0 = psqrt.MVNSqrt(base["m0"] + th[0], base["L0"] * torch.exp(th[1]))
+        q = psqrt.MVNSqrt(base["b"] * (1.0 + th[2]), base["cholQ"] * torch.exp(th[3]) +
+                          th[6] * torch.tril(torch.ones_like(base["cholQ"]), -1))
+        r = psqrt.MVNSqrt(base["c"] + th[4], base["cholR"] * torch.exp(th[5]))
+        return (x0, psqrt.FunctionalModel(lgssm.transition_function(case["F"]), q),
+                psqrt.FunctionalModel(lgssm.observation_function(case["H"]), r))
+
+    ell, grad = G.value_and_grad_reverse(build, theta0, ys, psqrt.linearization.extended)
+
+    def oracle_ell(th):
+        th = torch.as_tensor(th, dtype=torch.float64, device=_dev())
+        x0, tm, om = build(th)
+        c = dict(case)
+        c.update(m0=x0.mean.cpu().numpy(), L0=x0.chol.cpu().numpy(), b=tm.mvn.mean.cpu().numpy(),
+                 cholQ=tm.mvn.chol.cpu().numpy(), c=om.mvn.mean.cpu().numpy(), cholR=om.mvn.chol.cpu().numpy())
+        rep = lambda a: np.repeat(a[None], T, 0)
+        ssm = tuple(rep(c[k]) for k in ("F", "cholQ", "b", "H", "cholR", "c"))
+        ms = np.concatenate([c["m0"][None], np.zeros((T - 1, n))])
+        Ls = np.concatenate([c["L0"][None], np.zeros((T - 1, n, n))])
+        _, fm, fc, _, _ = O.associative_scan(O.sqrt_filtering_operator, O.sqrt_filtering_elements(*ssm, ms, Ls, c["ys"]))
+        fm = np.concatenate([c["m0"][None], fm])
+        fc = np.concatenate([c["L0"][None], fc])
+        return float(np.sum(O.sqrt_loglikelihood_terms(*ssm, fm[:-1], fc[:-1], c["ys"])))
+
+    assert abs(ell.item() - oracle_ell(theta0)) < 1e-8 * abs(ell.item())
+    h = 1e-5
+    for i in range(theta0.size):
+        e = np.zeros_like(theta0)
+        e[i] = h
+        fd = (oracle_ell(theta0 + e) - oracle_ell(theta0 - e)) / (2 * h)
+        assert abs(grad[i].item() - fd) < 2e-6 * max(1.0, abs(fd)), (i, grad[i].item(), fd)
+    # forward mode, one direction at a time, at the same (nominal-independent) model
+    ell_f, grad_f = G.value_and_grad(build, theta0, ys, psqrt.linearization.extended,
+                                     criterion=lambda i, *_: i < 1, implicit_terms=1)
+    assert abs(ell_f.item() - ell.item()) < 1e-10 * abs(ell.item())
+    assert rel_err(grad.cpu().numpy(), grad_f.cpu().numpy()) < 1e-8
