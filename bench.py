@@ -473,7 +473,8 @@ def run_psqrt(args):
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the psqrt arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa(local_rank) if world > 1 else None
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank)   # pinned buffers are first-touched on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -695,6 +696,7 @@ def run_psqrt(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only, bounded sample) -----------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, affinity0)    # the CPU baseline may use every host core again
         threads = os.cpu_count() or 1
         cpu_pass_rate(model, 5_000, threads)
         Tc = T if T <= 1_000_000 else 1_000_000
@@ -748,7 +750,7 @@ def run_psqrt(args):
         if parity is not None:
             line["parity"] = parity
         if numa is not None:
-            line["config"]["host_numa_node_rank0"] = numa
+            line["config"]["host_numa_node_rank0"] = numa   # the rank ran (and pinned its buffers) on this node
         if secondary:
             line["secondary"] = secondary
         print(json.dumps(line))

@@ -74,7 +74,8 @@ int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_
   if (T <= 0 || batch <= 0 || chunk_len < 0) return PSQRT_EINVAL;
   long long K = chunk_len;
   if (K == 0) {
-    long long per_seq = kTargetThreads / batch;
+    // sub-warp sweeps (psqrt_coopsweep.cuh): 8 lanes per chunk, two 256-thread CTAs per SM
+    long long per_seq = (ln->coop_mask() ? kTargetThreads / 4 : kTargetThreads) / batch;
     if (per_seq < 32) per_seq = 32;
     K = (T + per_seq - 1) / per_seq;
     if (K < kMinChunk) K = kMinChunk;
@@ -344,7 +345,7 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   // Without a peer exchange and for a single sequence the smoothing mid scan (K4) runs inside K3 on a few extra
   // CTAs, concurrently with the workers' step loops (psqrt_kernels.cuh, fused_smooth_mid); PSQRT_FUSE_MID=0: own kernel.
   static const bool fuse_env = [] { const char* e = getenv("PSQRT_FUSE_MID"); return e ? atoi(e) != 0 : true; }();
-  const bool fuse = smooth && !peer && batch == 1 && fuse_env;
+  const bool fuse = smooth && !peer && batch == 1 && fuse_env && !(c.ln->coop_mask() & 2);
   psq::FuseArgs fa;
   fa.group_s = c.ws.group_s; fa.stotal = stotal; fa.ctr = fuse ? c.ws.counter_x : nullptr;
   c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m,
@@ -408,7 +409,8 @@ int64_t psqrt_peer_layout(int nx, int n_ranks, int64_t batch, psqrt_peer* f, psq
 int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* fL, const double* carry_m,
                          const double* carry_L, int write_terminal, int nx, int64_t T, int64_t batch, int chunk_len,
                          double* sm, double* sL, void* ws, size_t ws_bytes, void* stream) {
-  (void)fm; (void)fL;  // identify the pass: psqrt_filter_apply left their packed copy in the workspace (psqrt.h)
+  // fm, fL: the per-thread backward sweep reads the packed copy psqrt_filter_apply left in the workspace (psqrt.h);
+  // the sub-warp form (nx = 6, 8) reads the trajectory itself
   if (!ssm_ok(ssm, false, nx, 0) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
   int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
@@ -417,7 +419,7 @@ int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* f
   bind_fused(a, c.ws, T);
   HostModel hmv;
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m, carry_L,
-                     nx, (long long)nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL,
+                     nx, (long long)nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, fm, fL, sm, sL,
                      write_terminal, (cudaStream_t)stream);
   return check_launch();
 }
@@ -443,8 +445,8 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
   HostModel hmv;
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
                      fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,
-                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL, 1,
-                     (cudaStream_t)stream);
+                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, fm, fL, sm,
+                     sL, 1, (cudaStream_t)stream);
   return check_launch();
 }
 
@@ -466,8 +468,8 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
                    nullptr, st);
   c.ln->smooth_apply(a, host_model(ssm, false, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch,
                      fm + (size_t)T * nx, fL + (size_t)T * nx * nx, (long long)(T + 1) * nx,
-                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, sm, sL, 1,
-                     st);
+                     (long long)(T + 1) * nx * nx, c.ws.chunk_suf, c.ws.warp_stot, c.ws.group_s, c.ws.fpack, fm, fL, sm,
+                     sL, 1, st);
   return check_launch();
 }
 

@@ -27,6 +27,13 @@ const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
 #if !PSQ_MID2
 #include "psqrt_coop.cuh"
 #endif
+// sub-warp sweeps (psqrt_coopsweep.cuh): compiled for the state dimensions whose per-thread sweeps spill
+#ifndef PSQ_COOP_SWEEPS
+#define PSQ_COOP_SWEEPS (PSQ_N == 6 || PSQ_N == 8)
+#endif
+#if PSQ_COOP_SWEEPS
+#include "psqrt_coopsweep.cuh"
+#endif
 
 #include <stdlib.h>
 #include <string.h>
@@ -165,12 +172,64 @@ inline int fuse_extra_ctas(long long work_ctas) {
   return (int)e;
 }
 
+// Which sweeps run in sub-warp form: PSQRT_COOP = bit mask (1 = K1, 2 = K3, 4 = K5), default all where compiled.
+inline int coop_mask() {
+#if PSQ_COOP_SWEEPS
+  static const int m = [] {
+    const char* e = getenv("PSQRT_COOP");
+    // measured on B200 (T = 1e6): nx = 8 5.9 -> 3.6 ms per pass in sub-warp form, nx = 6 1.49 -> 2.25 ms (its
+    // per-thread sweeps spill little, and two of its eight lanes idle): on by default at nx = 8 only
+    return e ? (atoi(e) & 7) : (PSQ_N == 8 ? 7 : 0);
+  }();
+  return m;
+#else
+  return 0;
+#endif
+}
+#if PSQ_COOP_SWEEPS
+inline dim3 coop_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kCChunks), (unsigned)B, 1); }
+inline bool even(long long v) { return (v & 1) == 0; }
+// 16-byte global accesses of the sub-warp sweeps: even N, every base 16-byte aligned, every stride even
+inline int coop_vec(const SSMArgs& a, bool obs, const void* p0, const void* p1, const void* p2, const void* p3) {
+  if (N % 2) return 0;
+  bool ok = aligned16(a.F) && aligned16(a.Q) && even(a.tF) && even(a.tQ) && even(a.sF) && even(a.sQ);
+  if (obs) ok = ok && aligned16(a.H) && even(a.tH) && even(a.sH);
+  ok = ok && aligned16(p0) && aligned16(p1) && aligned16(p2) && aligned16(p3);
+  return ok ? 1 : 0;
+}
+template <class OP, int NF, bool REV>
+void unit_scan(double* items, long long Ppad, long long B, double* unit_tot, unsigned int* counter,
+               unsigned int* fuse_ctr, cudaStream_t st) {
+  constexpr size_t smem = unit_scan_smem_bytes<OP, NF>();
+  static_assert(smem <= 227 * 1024, "unit scan: shared memory budget");
+  auto kern = k_unit_scan<OP, NF, REV>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<coop_grid(Ppad, B), 32 * OP::G, smem, st>>>(items, Ppad, unit_tot, counter, fuse_ctr);
+}
+template <class KERN>
+void coop_smem(KERN kern) {
+  constexpr size_t smem = CoopSweep<N>::smem_bytes();
+  static_assert(smem <= 113 * 1024, "two CTAs of a sub-warp sweep per SM");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+#endif
+
 template <int NY>
 struct NYImpl {
   static void filter_reduce(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                             double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter,
                             unsigned int* fuse_ctr, cudaStream_t st) {
     const size_t ysmem = LaneRing<NY, kYDepth>::smem_bytes(kBlock);
+#if PSQ_COOP_SWEEPS
+    if ((coop_mask() & 1) && !a.fused) {
+      auto kern = k_coop_filter_reduce<N, NY>;
+      coop_smem(kern);
+      kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
+                                                                            coop_vec(a, true, 0, 0, 0, 0));
+      unit_scan<CoopF2<N>, FElem<N>::NF, false>(chunk_pref, Ppad, B, warp_tot, counter, fuse_ctr, st);
+      return;
+    }
+#endif
 #if PSQ_N == 5
     if constexpr (NY == 2) {
       if (a.fused) {
@@ -215,10 +274,38 @@ struct NYImpl {
 #undef PSQ_K3
   }
   static void filter_apply(int smooth, const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad,
-                           long long B, const double* cm, const double* cL, const double* chunk_own,
+                           long long B, const double* cm, const double* cL, double* chunk_own,
                            const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
                            double* fL, double* chunk_suf, double* warp_stot, double* ell_part,
                            unsigned int* counter_s, double* fpack, const FuseArgs* fuse, cudaStream_t st) {
+#if PSQ_COOP_SWEEPS
+    if ((coop_mask() & 2) && !a.fused) {
+      // once per chunk: start states (parked in chunk_own), smoothing totals; then the sub-warp step loop
+      if (smooth) {
+        k_chunk_start<N, true><<<coop_grid(Ppad, B), 32, 0, st>>>(T, K, Ppad, cm, cL, chunk_own, chunk_pref, warp_pref,
+                                                                  group_pref, fm, fL, chunk_suf, counter_s);
+        unit_scan<CoopS2<N>, SElem<N>::NF, true>(chunk_suf, Ppad, B, warp_stot, nullptr, nullptr, st);
+      } else {
+        k_chunk_start<N, false><<<coop_grid(Ppad, B), 32, 0, st>>>(T, K, Ppad, cm, cL, chunk_own, chunk_pref, warp_pref,
+                                                                   group_pref, fm, fL, chunk_suf, counter_s);
+      }
+      double* const fp = (smooth && !(coop_mask() & 4)) ? fpack : nullptr;   // only the per-thread K5 reads it
+      const int vec = coop_vec(a, true, fm, fL, 0, 0);
+      const long long css = (long long)FElem<N>::NF * Ppad;
+      if (ell_part) {
+        auto kern = k_coop_filter_apply<N, NY, true>;
+        coop_smem(kern);
+        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm, fL,
+                                                                              ell_part, fp, vec);
+      } else {
+        auto kern = k_coop_filter_apply<N, NY, false>;
+        coop_smem(kern);
+        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm, fL,
+                                                                              ell_part, fp, vec);
+      }
+      return;
+    }
+#endif
 #define PSQ_FA(SM, SRCV)                                                                                             \
   do {                                                                                                               \
     if (ell_part)                                                                                                    \
@@ -411,9 +498,20 @@ void smooth_apply_t(const SRC& src, long long T, int K, long long Ppad, long lon
 #undef PSQ_K5
 }
 void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, long long Ppad, long long B,
-                  const double* cm, const double* cL, long long cms, long long cLs, const double* chunk_suf,
-                  const double* warp_suf, const double* group_suf, const double* fpack, double* sm, double* sL,
-                  int write_terminal, cudaStream_t st) {
+                  const double* cm, const double* cL, long long cms, long long cLs, double* chunk_suf,
+                  const double* warp_suf, const double* group_suf, const double* fpack, const double* fm,
+                  const double* fL, double* sm, double* sL, int write_terminal, cudaStream_t st) {
+#if PSQ_COOP_SWEEPS
+  if ((coop_mask() & 4) && !a.fused && fm && fL) {
+    k_chunk_end<N><<<coop_grid(Ppad, B), 32, 0, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, sm,
+                                                      sL, write_terminal);
+    auto kern = k_coop_smooth_apply<N>;
+    coop_smem(kern);
+    kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(
+        a, T, K, Ppad, chunk_suf, (long long)SElem<N>::NF * Ppad, fm, fL, sm, sL, coop_vec(a, false, fm, fL, sm, sL));
+    return;
+  }
+#endif
 #if PSQ_N == 5
   if (a.fused) {
     smooth_apply_t(make_src_fusedT(a), T, K, Ppad, B, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, fpack, sm, sL,
@@ -508,7 +606,8 @@ const LaunchN kTable = {N,
                         nullptr,
 #endif
                         &tria,
-                        &chol_update};
+                        &chol_update,
+                        &coop_mask};
 
 }  // namespace
 

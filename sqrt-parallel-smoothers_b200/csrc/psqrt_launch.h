@@ -39,7 +39,7 @@ struct LaunchNY {
                         double* chunk_own, double* chunk_pref, double* warp_tot, unsigned int* counter,
                         unsigned int* fuse_ctr, cudaStream_t);
   void (*filter_apply)(int smooth, const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
-                       const double* carry_m, const double* carry_L, const double* chunk_own,
+                       const double* carry_m, const double* carry_L, double* chunk_own,
                        const double* chunk_pref, const double* warp_pref, const double* group_pref, double* fm,
                        double* fL, double* chunk_suf, double* warp_stot, double* ell_part, unsigned int* counter_s,
                        double* fpack, const FuseArgs* fuse, cudaStream_t);
@@ -61,10 +61,12 @@ struct LaunchN {
   void (*smooth_reduce)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B, const double* fm,
                         const double* fL, double* chunk_suf, double* warp_stot, unsigned int* counter, double* fpack,
                         cudaStream_t);
+  // chunk_suf is an in/out scratch (the sub-warp form parks the per-chunk start states in it); fm, fL: the filtered
+  // trajectory of the pass (read by the sub-warp form instead of fpack)
   void (*smooth_apply)(const SSMArgs&, const HostModel* hm, long long T, int K, long long Ppad, long long B,
                        const double* carry_m, const double* carry_L, long long cms, long long cLs,
-                       const double* chunk_suf, const double* warp_suf, const double* group_suf, const double* fpack,
-                       double* sm, double* sL, int write_terminal, cudaStream_t);
+                       double* chunk_suf, const double* warp_suf, const double* group_suf, const double* fpack,
+                       const double* fm, const double* fL, double* sm, double* sL, int write_terminal, cudaStream_t);
   // pc != nullptr: wait for all ranks' pass number, then fold the totals out of the local exchange buffer
   void (*carry_filter)(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                        double* cL, const PeerCtx* pc, cudaStream_t);
@@ -92,6 +94,8 @@ struct LaunchN {
   void (*fused_prepare)(const SSMArgs&, long long T, long long B, cudaStream_t);
   void (*tria)(const double* A, double* L, int cols, long long batch, cudaStream_t);
   void (*chol_update)(double* L, const double* V, int k, double alpha, long long batch, cudaStream_t);
+  // bit mask of the sweeps that run in sub-warp form (psqrt_coopsweep.cuh): 1 = K1, 2 = K3, 4 = K5; 0 = per-thread
+  int (*coop_mask)();
 };
 
 // defined by the per-nx translation units (psqrt_inst.cu compiled with -DPSQ_N=<nx>)
