@@ -28,6 +28,17 @@ namespace psq {
 constexpr int kCG = 8;                     // lanes per chunk
 constexpr int kCChunks = 32;               // chunks per CTA (= one scan unit of 32 chunks)
 constexpr int kCBlock = kCG * kCChunks;    // 256 threads
+// resident CTAs per SM requested from ptxas for the sub-warp step loops (2: 128 registers, 1: 255); measured A/B in
+// DESIGN.md section 5
+#ifndef PSQ_COOP_MINB_K1
+#define PSQ_COOP_MINB_K1 1
+#endif
+#ifndef PSQ_COOP_MINB_K3
+#define PSQ_COOP_MINB_K3 2
+#endif
+#ifndef PSQ_COOP_MINB_K5
+#define PSQ_COOP_MINB_K5 2
+#endif
 
 template <int N>
 struct CoopSweep {
@@ -253,7 +264,7 @@ struct CoopModel {
 // the backward sweep is the per-thread kernel -- the packed filtered states it reads (fpack).
 // =================================================================================================================
 template <int N, int NY, bool LOGLIK>
-__global__ void __launch_bounds__(kCBlock, 2)
+__global__ void __launch_bounds__(kCBlock, PSQ_COOP_MINB_K3)
 k_coop_filter_apply(const SSMArgs a, long long T, int K, long long Ppad, const double* __restrict__ cstate,
                     long long cs_stride, double* __restrict__ fm, double* __restrict__ fL,
                     double* __restrict__ ell_part, double* __restrict__ fpack, const int vec_i) {
@@ -400,7 +411,7 @@ k_coop_filter_apply(const SSMArgs a, long long T, int K, long long Ppad, const d
 // layout is already coalesced for this mapping and no packed copy is needed).
 // =================================================================================================================
 template <int N>
-__global__ void __launch_bounds__(kCBlock, 2)
+__global__ void __launch_bounds__(kCBlock, PSQ_COOP_MINB_K5)
 k_coop_smooth_apply(const SSMArgs a, long long T, int K, long long Ppad, const double* __restrict__ cstate,
                     long long cs_stride, const double* __restrict__ fm, const double* __restrict__ fL,
                     double* __restrict__ sm, double* __restrict__ sL, const int vec_i) {
@@ -529,7 +540,7 @@ k_coop_smooth_apply(const SSMArgs a, long long T, int K, long long Ppad, const d
 // reads) and the full summary to `summ` (FElem order, SoA [NF][Ppad]), which k_chunk_scan_f scans in place.
 // =================================================================================================================
 template <int N, int NY>
-__global__ void __launch_bounds__(kCBlock, 2)
+__global__ void __launch_bounds__(kCBlock, PSQ_COOP_MINB_K1)
 k_coop_filter_reduce(const SSMArgs a, long long T, int K, long long Ppad, double* __restrict__ chunk_own,
                      double* __restrict__ summ, const int vec_i) {
   const bool vec = vec_i != 0;

@@ -329,6 +329,9 @@ def filter_smoother(ssm: LinearizedSSM, y: torch.Tensor, m0: torch.Tensor, L0: t
         fm, fL = fm[0], fL[0]
         sm, sL = (sm[0], sL[0]) if smooth else (None, None)
         ell = ell[0] if loglik else None
+    fL._psqrt_lower = True      # written by the kernels with exactly zero upper triangles
+    if sL is not None:
+        sL._psqrt_lower = True
     return fm, fL, sm, sL, ell
 
 

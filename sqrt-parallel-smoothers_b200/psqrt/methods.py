@@ -205,7 +205,8 @@ def smoothing(transition_model, filter_trajectory, linearization_method: Callabl
         nominal = _default_nominal(T1, nx, dev)
     ssm = _linearize(linearization_method, transition_model, None, nominal)
     fL = ft.chol
-    if bool((torch.triu(fL, 1) != 0).any()):      # kernels read lower triangles only
+    # kernels read lower triangles only; factors this library wrote are tagged (no device round trip to find out)
+    if not getattr(fL, "_psqrt_lower", False) and bool((torch.triu(fL, 1) != 0).any()):
         fL = _lib.tria(fL)
     sm, sL = _lib.smoother(ssm, ft.mean, fL)
     return MVNSqrt(sm, sL)
@@ -256,7 +257,8 @@ def sampling(key, n_samples: int, transition_model, filter_trajectory, lineariza
     nominal = _mvn(nominal_trajectory, dev)
     ssm = _linearize(linearization_method, transition_model, None, nominal)
     fL = ft.chol
-    if bool((torch.triu(fL, 1) != 0).any()):      # kernels read lower triangles only
+    # kernels read lower triangles only; factors this library wrote are tagged (no device round trip to find out)
+    if not getattr(fL, "_psqrt_lower", False) and bool((torch.triu(fL, 1) != 0).any()):
         fL = _lib.tria(fL)
     shape = (T1, int(n_samples), nx)
     if isinstance(key, (np.ndarray, torch.Tensor)) and tuple(key.shape) == shape:
