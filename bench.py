@@ -590,31 +590,48 @@ def run_psqrt(args):
     value = T * world / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------
+    # Host buffers are pinned; the D2H of pass i runs on a copy stream into one of two result buffers while the H2D
+    # and the kernels of pass i + 1 proceed on the compute stream (PCIe is full duplex).  Every pass's inputs and
+    # results cross the bus inside the timed region, which ends when the last result has landed on the host.
     ys_host = torch.as_tensor(ys_np).pin_memory()
-    out_m = torch.empty((T + 1, NX), dtype=torch.float64).pin_memory()
-    out_L = torch.empty((T + 1, NX, NX), dtype=torch.float64).pin_memory()
+    out_m = [torch.empty((T + 1, NX), dtype=torch.float64).pin_memory() for _ in range(2)]
+    out_L = [torch.empty((T + 1, NX, NX), dtype=torch.float64).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    e2e_count = [0]
 
     def e2e_pass():
         if world > 1:
             # the sharded pass replays from its CUDA graph on the static input buffer: H2D into that buffer, replay,
-            # D2H of the smoothed shard
+            # D2H of the smoothed shard (static result buffers: the copy must finish before the next replay)
             ys.copy_(ys_host, non_blocking=True)
             fm, fL, sm, sL, _ = one_pass()
-        else:
-            y_dev = ys_host.to(dev, non_blocking=True)
-            res = psqrt.filter_smoother(y_dev, x0, tm, om, psqrt.linearization.extended, None, True)
-            sm, sL = res.mean, res.chol
-        out_m.copy_(sm.reshape(out_m.shape), non_blocking=True)
-        out_L.copy_(sL.reshape(out_L.shape), non_blocking=True)
+            out_m[0].copy_(sm.reshape(out_m[0].shape), non_blocking=True)
+            out_L[0].copy_(sL.reshape(out_L[0].shape), non_blocking=True)
+            return
+        y_dev = ys_host.to(dev, non_blocking=True)
+        res = psqrt.filter_smoother(y_dev, x0, tm, om, psqrt.linearization.extended, None, True)
+        sm, sL = res.mean, res.chol
+        done = torch.cuda.Event()
+        done.record()
+        i = e2e_count[0] & 1
+        e2e_count[0] += 1
+        copy_stream.wait_event(done)
+        with torch.cuda.stream(copy_stream):
+            out_m[i].copy_(sm.reshape(out_m[i].shape), non_blocking=True)
+            out_L[i].copy_(sL.reshape(out_L[i].shape), non_blocking=True)
+        sm.record_stream(copy_stream)
+        sL.record_stream(copy_stream)
 
     for _ in range(2):
         e2e_pass()
+    copy_stream.synchronize()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_e2e = max(3, min(args.steps, 10))
     e2.record()
     for _ in range(n_e2e):
         e2e_pass()
+    torch.cuda.current_stream().wait_stream(copy_stream)   # the timed region ends after the last D2H
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -626,7 +643,9 @@ def run_psqrt(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e = {"value": T * world / (ms_e2e * 1e-3), "unit": "steps/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": int(ys_host.numel() * 8) * world,
-           "d2h_bytes_per_step": int((out_m.numel() + out_L.numel()) * 8) * world}
+           "d2h_bytes_per_step": int((out_m[0].numel() + out_L[0].numel()) * 8) * world,
+           "overlap": ("D2H of pass i on a copy stream (two pinned result buffers) under the H2D + kernels of pass i + 1"
+                       if world == 1 else "none (static graph buffers)")}
 
     # ---- per-kernel-stage timing for the roofline (staged C-ABI calls, same kernels) -------------
     roofline = None

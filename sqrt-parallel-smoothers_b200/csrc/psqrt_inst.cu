@@ -34,6 +34,13 @@ const LaunchN* PSQ_CAT(launch_n, PSQ_N)() { return nullptr; }
 #if PSQ_COOP_SWEEPS
 #include "psqrt_coopsweep.cuh"
 #endif
+// two rows per lane (psqrt_coopsweep2.cuh): nx = 8 on groups of 4 lanes
+#ifndef PSQ_COOP_ROWS2
+#define PSQ_COOP_ROWS2 (PSQ_N == 8)
+#endif
+#if PSQ_COOP_SWEEPS && PSQ_COOP_ROWS2
+#include "psqrt_coopsweep2.cuh"
+#endif
 
 #include <stdlib.h>
 #include <string.h>
@@ -186,6 +193,18 @@ inline int coop_mask() {
   return 0;
 #endif
 }
+// lanes per chunk of the sub-warp sweeps: PSQRT_COOP_G = 4 (two rows per lane, where compiled: nx = 8) or 8
+inline int coop_lanes() {
+#if PSQ_COOP_SWEEPS && PSQ_COOP_ROWS2
+  static const int g = [] {
+    const char* e = getenv("PSQRT_COOP_G");
+    return (e && atoi(e) == 8) ? 8 : 4;
+  }();
+  return g;
+#else
+  return 8;
+#endif
+}
 #if PSQ_COOP_SWEEPS
 inline dim3 coop_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kCChunks), (unsigned)B, 1); }
 inline bool even(long long v) { return (v & 1) == 0; }
@@ -222,10 +241,20 @@ struct NYImpl {
     const size_t ysmem = LaneRing<NY, kYDepth>::smem_bytes(kBlock);
 #if PSQ_COOP_SWEEPS
     if ((coop_mask() & 1) && !a.fused) {
-      auto kern = k_coop_filter_reduce<N, NY>;
-      coop_smem(kern);
-      kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
-                                                                            coop_vec(a, true, 0, 0, 0, 0));
+#if PSQ_COOP_ROWS2
+      if (coop_lanes() == 4) {
+        auto kern = k_coopr_filter_reduce<N, NY, 4>;
+        coop_smem(kern);
+        kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
+                                                                                   coop_vec(a, true, 0, 0, 0, 0));
+      } else
+#endif
+      {
+        auto kern = k_coop_filter_reduce<N, NY>;
+        coop_smem(kern);
+        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
+                                                                              coop_vec(a, true, 0, 0, 0, 0));
+      }
       unit_scan<CoopF2<N>, FElem<N>::NF, false>(chunk_pref, Ppad, B, warp_tot, counter, fuse_ctr, st);
       return;
     }
@@ -292,6 +321,22 @@ struct NYImpl {
       double* const fp = (smooth && !(coop_mask() & 4)) ? fpack : nullptr;   // only the per-thread K5 reads it
       const int vec = coop_vec(a, true, fm, fL, 0, 0);
       const long long css = (long long)FElem<N>::NF * Ppad;
+#if PSQ_COOP_ROWS2
+      if (coop_lanes() == 4) {
+        if (ell_part) {
+          auto kern = k_coopr_filter_apply<N, NY, 4, true>;
+          coop_smem(kern);
+          kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm,
+                                                                                     fL, ell_part, fp, vec);
+        } else {
+          auto kern = k_coopr_filter_apply<N, NY, 4, false>;
+          coop_smem(kern);
+          kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm,
+                                                                                     fL, ell_part, fp, vec);
+        }
+        return;
+      }
+#endif
       if (ell_part) {
         auto kern = k_coop_filter_apply<N, NY, true>;
         coop_smem(kern);
@@ -505,6 +550,15 @@ void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, lon
   if ((coop_mask() & 4) && !a.fused && fm && fL) {
     k_chunk_end<N><<<coop_grid(Ppad, B), 32, 0, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, sm,
                                                       sL, write_terminal);
+#if PSQ_COOP_ROWS2
+    if (coop_lanes() == 4) {
+      auto kern = k_coopr_smooth_apply<N, 4>;
+      coop_smem(kern);
+      kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(
+          a, T, K, Ppad, chunk_suf, (long long)SElem<N>::NF * Ppad, fm, fL, sm, sL, coop_vec(a, false, fm, fL, sm, sL));
+      return;
+    }
+#endif
     auto kern = k_coop_smooth_apply<N>;
     coop_smem(kern);
     kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(
