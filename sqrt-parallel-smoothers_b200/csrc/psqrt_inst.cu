@@ -184,8 +184,9 @@ inline int coop_mask() {
 #if PSQ_COOP_SWEEPS
   static const int m = [] {
     const char* e = getenv("PSQRT_COOP");
-    // measured on B200 (T = 1e6): nx = 8 5.9 -> 3.6 ms per pass in sub-warp form, nx = 6 1.49 -> 2.25 ms (its
-    // per-thread sweeps spill little, and two of its eight lanes idle): on by default at nx = 8 only
+    // measured on B200 (T = 1e6): nx = 8 5.9 -> 2.7 ms per pass in sub-warp form (two rows per lane), nx = 6
+    // 1.49 -> 2.25 ms (its per-thread sweeps spill little, and two of its eight lanes idle): on by default at
+    // nx = 8 only
     return e ? (atoi(e) & 7) : (PSQ_N == 8 ? 7 : 0);
   }();
   return m;
@@ -193,19 +194,9 @@ inline int coop_mask() {
   return 0;
 #endif
 }
-// lanes per chunk of the sub-warp sweeps: PSQRT_COOP_G = 4 (two rows per lane, where compiled: nx = 8) or 8
-inline int coop_lanes() {
-#if PSQ_COOP_SWEEPS && PSQ_COOP_ROWS2
-  static const int g = [] {
-    const char* e = getenv("PSQRT_COOP_G");
-    return (e && atoi(e) == 8) ? 8 : 4;
-  }();
-  return g;
-#else
-  return 8;
-#endif
-}
 #if PSQ_COOP_SWEEPS
+// lanes per chunk: 4 with two matrix rows per lane (nx = 8), 8 with one row per lane
+constexpr int kCoopLanes = PSQ_COOP_ROWS2 ? 4 : kCG;
 inline dim3 coop_grid(long long Ppad, long long B) { return dim3((unsigned)(Ppad / kCChunks), (unsigned)B, 1); }
 inline bool even(long long v) { return (v & 1) == 0; }
 // 16-byte global accesses of the sub-warp sweeps: even N, every base 16-byte aligned, every stride even
@@ -241,19 +232,15 @@ struct NYImpl {
     const size_t ysmem = LaneRing<NY, kYDepth>::smem_bytes(kBlock);
 #if PSQ_COOP_SWEEPS
     if ((coop_mask() & 1) && !a.fused) {
-#if PSQ_COOP_ROWS2
-      if (coop_lanes() == 4) {
-        auto kern = k_coopr_filter_reduce<N, NY, 4>;
-        coop_smem(kern);
-        kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
-                                                                                   coop_vec(a, true, 0, 0, 0, 0));
-      } else
-#endif
       {
+#if PSQ_COOP_ROWS2
+        auto kern = k_coopr_filter_reduce<N, NY, kCoopLanes>;   // two rows per lane (psqrt_coopsweep2.cuh)
+#else
         auto kern = k_coop_filter_reduce<N, NY>;
+#endif
         coop_smem(kern);
-        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, chunk_pref,
-                                                                              coop_vec(a, true, 0, 0, 0, 0));
+        kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(
+            a, T, K, Ppad, chunk_own, chunk_pref, coop_vec(a, true, 0, 0, 0, 0));
       }
       unit_scan<CoopF2<N>, FElem<N>::NF, false>(chunk_pref, Ppad, B, warp_tot, counter, fuse_ctr, st);
       return;
@@ -321,32 +308,24 @@ struct NYImpl {
       double* const fp = (smooth && !(coop_mask() & 4)) ? fpack : nullptr;   // only the per-thread K5 reads it
       const int vec = coop_vec(a, true, fm, fL, 0, 0);
       const long long css = (long long)FElem<N>::NF * Ppad;
-#if PSQ_COOP_ROWS2
-      if (coop_lanes() == 4) {
-        if (ell_part) {
-          auto kern = k_coopr_filter_apply<N, NY, 4, true>;
-          coop_smem(kern);
-          kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm,
-                                                                                     fL, ell_part, fp, vec);
-        } else {
-          auto kern = k_coopr_filter_apply<N, NY, 4, false>;
-          coop_smem(kern);
-          kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm,
-                                                                                     fL, ell_part, fp, vec);
-        }
-        return;
-      }
-#endif
       if (ell_part) {
+#if PSQ_COOP_ROWS2
+        auto kern = k_coopr_filter_apply<N, NY, kCoopLanes, true>;
+#else
         auto kern = k_coop_filter_apply<N, NY, true>;
+#endif
         coop_smem(kern);
-        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm, fL,
-                                                                              ell_part, fp, vec);
+        kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own,
+                                                                                          css, fm, fL, ell_part, fp, vec);
       } else {
+#if PSQ_COOP_ROWS2
+        auto kern = k_coopr_filter_apply<N, NY, kCoopLanes, false>;
+#else
         auto kern = k_coop_filter_apply<N, NY, false>;
+#endif
         coop_smem(kern);
-        kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own, css, fm, fL,
-                                                                              ell_part, fp, vec);
+        kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(a, T, K, Ppad, chunk_own,
+                                                                                          css, fm, fL, ell_part, fp, vec);
       }
       return;
     }
@@ -551,17 +530,12 @@ void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, lon
     k_chunk_end<N><<<coop_grid(Ppad, B), 32, 0, st>>>(T, K, Ppad, cm, cL, cms, cLs, chunk_suf, warp_suf, group_suf, sm,
                                                       sL, write_terminal);
 #if PSQ_COOP_ROWS2
-    if (coop_lanes() == 4) {
-      auto kern = k_coopr_smooth_apply<N, 4>;
-      coop_smem(kern);
-      kern<<<coop_grid(Ppad, B), kCChunks * 4, CoopSweep<N>::smem_bytes(), st>>>(
-          a, T, K, Ppad, chunk_suf, (long long)SElem<N>::NF * Ppad, fm, fL, sm, sL, coop_vec(a, false, fm, fL, sm, sL));
-      return;
-    }
-#endif
+    auto kern = k_coopr_smooth_apply<N, kCoopLanes>;
+#else
     auto kern = k_coop_smooth_apply<N>;
+#endif
     coop_smem(kern);
-    kern<<<coop_grid(Ppad, B), kCBlock, CoopSweep<N>::smem_bytes(), st>>>(
+    kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(
         a, T, K, Ppad, chunk_suf, (long long)SElem<N>::NF * Ppad, fm, fL, sm, sL, coop_vec(a, false, fm, fL, sm, sL));
     return;
   }
