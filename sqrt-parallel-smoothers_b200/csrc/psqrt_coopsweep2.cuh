@@ -214,11 +214,6 @@ __device__ __forceinline__ void coop_update_reflectors_rows(double (&hrow)[N + N
   });
 }
 
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-
 // Model rows of one step: rows l + s G of F, Q, bq; row l of H, R and entry l of c on the lanes l < NY
 template <int N, int NY, int G, int R>
 struct CoopModelR {
@@ -243,13 +238,6 @@ struct CoopModelR {
     for (int j = 0; j < N; ++j) H[j] = h ? H[j] : 0.0;
     c = h ? a.c[seq * a.sc + k * a.tc + la] : 0.0;
   }
-};
-
-// K5's prefetch buffers: per group two slots of N rows (stride RS) + N means
-template <int N>
-struct CoopSweepPF {
-  static constexpr int PFS = N * CoopSweep<N>::RS + 8;
-  static constexpr size_t smem_bytes() { return CoopSweep<N>::smem_bytes() + sizeof(double) * 2 * PFS * kCChunks; }
 };
 
 #ifndef PSQ_COOPR_MINB_K1
@@ -313,16 +301,13 @@ k_coopr_filter_apply(const SSMArgs a, long long T, int K, long long Ppad, const 
   const bool tv_t = (a.tF | a.tQ | a.tb) != 0, tv_o = (a.tH | a.tR | a.tc) != 0;
   CoopModelR<N, NY, G, R> md;
   double ell = 0.0;
-  const double* const yp = a.y + seq * a.sy + ((l < NY) ? l : 0);
-  double ynext = (len > 0) ? yp[k0 * a.ty] : 0.0;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
     const bool act = j < len;
     const long long k = act ? k0 + j : 0;
     if (j == 0 || tv_t) md.load_transition(a, seq, k, l, vec);
     if (j == 0 || tv_o) md.load_observation(a, seq, k, l, vec);
-    const double yv = (l < NY) ? ynext : 0.0;
-    ynext = (j + 1 < len) ? yp[(k + 1) * a.ty] : 0.0;   // the next step's observation, one iteration ahead
+    const double yv = (l < NY) ? a.y[seq * a.sy + k * a.ty + l] : 0.0;
     // ---- predict
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -477,51 +462,23 @@ k_coopr_smooth_apply(const SSMArgs a, long long T, int K, long long Ppad, const 
   double* const sLS = sL + seq * (T + 1) * N * N;
   const bool tv_t = (a.tF | a.tQ | a.tb) != 0;
   CoopModelR<N, 1, G, R> md;
-  // The filtered rows of a step arrive by cp.async in one of two per-group buffers (rows at rs * RS, means behind
-  // them) while the previous step computes: no destination registers, no exposed load latency; the buffer then
-  // serves directly as the gather buffer of F L.  8-byte-aligned trajectories (vec = false) are copied synchronously.
-  constexpr int PFS = CoopSweepPF<N>::PFS;
-  double* const pf0 = coop_sm + kCChunks * CS::SZ + g * 2 * PFS;
-  auto fetch = [&](double* dst, long long kf) {
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-      const int rs = l + s * G;
-      const double* src = fLS + (kf * N + rs) * N;
-      if (vec) {
-#pragma unroll
-        for (int q = 0; q < N; q += 2) cp_async16(dst + rs * RS + q, src + q);
-        cp_async8(dst + N * RS + rs, fmS + kf * N + rs);
-      } else {
-#pragma unroll
-        for (int q = 0; q < N; ++q) dst[rs * RS + q] = src[q];
-        dst[N * RS + rs] = fmS[kf * N + rs];
-      }
-    }
-  };
-  if (K - 1 < len) fetch(pf0, k0 + K - 1);
-  cp_async_commit();
-  int cur = 0;
 #pragma unroll 1
   for (int jj = 0; jj < K; ++jj) {
     const int j = K - 1 - jj;
     const bool act = j < len;
     const long long k = act ? k0 + j : 0;
     if (jj == 0 || tv_t) md.load_transition(a, seq, k, l, vec);
-    double* const pfc = pf0 + cur * PFS;
-    cp_async_wait<0>();
-    if (j >= 1 && j - 1 < len) fetch(pf0 + (cur ^ 1) * PFS, k0 + j - 1);
-    cp_async_commit();
-    cur ^= 1;
-#pragma unroll
-    for (int s = 0; s < R; ++s) st_row<N>(buf + CS::R1 + (l + s * G) * RS, Ls[s]);
-    __syncwarp();
     double Lf[R][N], mf[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rs = l + s * G;
-      ld_row<N>(pfc + rs * RS, Lf[s]);
-      mf[s] = pfc[N * RS + rs];
+      gld_row<N>(fLS + (k * N + rs) * N, Lf[s], vec);
+      mf[s] = fmS[k * N + rs];
+      st_row<N>(buf + CS::R0 + rs * RS, Lf[s]);
+      st_row<N>(buf + CS::R1 + rs * RS, Ls[s]);
+      buf[CS::V0 + rs] = mf[s];
     }
+    __syncwarp();
     double top[R][2 * N], bot[R][2 * N], mpf[R];
 #pragma unroll
     for (int s = 0; s < R; ++s) {
@@ -532,8 +489,8 @@ k_coopr_smooth_apply(const SSMArgs a, long long T, int K, long long Ppad, const 
 #pragma unroll
     for (int kk = 0; kk < N; ++kk) {
       double t[N];
-      ld_row<N>(pfc + kk * RS, t);
-      const double mk = pfc[N * RS + kk];
+      ld_row<N>(buf + CS::R0 + kk * RS, t);
+      const double mk = buf[CS::V0 + kk];
 #pragma unroll
       for (int s = 0; s < R; ++s) {
         const double f = md.F[s][kk];
@@ -664,16 +621,13 @@ k_coopr_filter_reduce(const SSMArgs a, long long T, int K, long long Ppad, doubl
   double* const own = chunk_own + seq * NF * Ppad + c;
   const bool tv_t = (a.tF | a.tQ | a.tb) != 0, tv_o = (a.tH | a.tR | a.tc) != 0;
   CoopModelR<N, NY, G, R> md;
-  const double* const yp = a.y + seq * a.sy + ((l < NY) ? l : 0);
-  double ynext = (len > 0) ? yp[k0 * a.ty] : 0.0;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
     const bool act = j < len;
     const long long k = act ? k0 + j : 0;
     if (j == 0 || tv_t) md.load_transition(a, seq, k, l, vec);
     if (j == 0 || tv_o) md.load_observation(a, seq, k, l, vec);
-    const double yv = (l < NY) ? ynext : 0.0;
-    ynext = (j + 1 < len) ? yp[(k + 1) * a.ty] : 0.0;   // the next step's observation, one iteration ahead
+    const double yv = (l < NY) ? a.y[seq * a.sy + k * a.ty + l] : 0.0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rs = l + s * G;

@@ -531,15 +531,11 @@ void smooth_apply(const SSMArgs& a, const HostModel* hm, long long T, int K, lon
                                                       sL, write_terminal);
 #if PSQ_COOP_ROWS2
     auto kern = k_coopr_smooth_apply<N, kCoopLanes>;
-    constexpr size_t k5smem = CoopSweepPF<N>::smem_bytes();   // + the prefetch buffers of the filtered rows
-    static_assert(k5smem <= 113 * 1024, "two CTAs of the backward sweep per SM");
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5smem);
 #else
     auto kern = k_coop_smooth_apply<N>;
-    constexpr size_t k5smem = CoopSweep<N>::smem_bytes();
-    coop_smem(kern);
 #endif
-    kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, k5smem, st>>>(
+    coop_smem(kern);
+    kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(
         a, T, K, Ppad, chunk_suf, (long long)SElem<N>::NF * Ppad, fm, fL, sm, sL, coop_vec(a, false, fm, fL, sm, sL));
     return;
   }
