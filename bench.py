@@ -854,21 +854,22 @@ def run_bearings(args):
         for _ in range(max(args.warmup, 2)):
             run_grad()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            nom, ell, dell = run_grad()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        def median_ms(fn):   # one event pair per call, median (see the note at the primal timing below)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            out = None
+            for a, b in evs:
+                a.record()
+                out = fn()
+                b.record()
+            torch.cuda.synchronize()
+            t = sorted(a.elapsed_time(b) for a, b in evs)
+            return (t[len(t) // 2] if len(t) % 2 else 0.5 * (t[len(t) // 2 - 1] + t[len(t) // 2])), out
+
+        ms, (nom, ell, dell) = median_ms(run_grad)
         # the primal alone, for the cost of the gradient relative to the value
-        e0.record()
-        for _ in range(args.steps):
-            psqrt.iterated_smoothing(ys_d, x0, tm, om_pe, lin, nominal, True, criterion=lambda i, *_: i < n_iter,
-                                     return_loglikelihood=True)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_val = e0.elapsed_time(e1) / args.steps
+        ms_val, _ = median_ms(lambda: psqrt.iterated_smoothing(ys_d, x0, tm, om_pe, lin, nominal, True,
+                                                               criterion=lambda i, *_: i < n_iter,
+                                                               return_loglikelihood=True))
         hfd = 1e-4 * prec   # check of the device gradient: central difference of the primal path itself
         ells = [float(psqrt.iterated_smoothing(ys_d, x0, tm, om_of(prec + sgn * hfd), lin, nominal, True,
                                                criterion=lambda i, *_: i < n_iter, return_loglikelihood=True)[1])
@@ -903,13 +904,18 @@ def run_bearings(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
+    # one event pair per call, median reported: the host loop of an iterated smoother (~50 launches per iteration) is
+    # exposed to scheduling hiccups of a busy host, and one 40 ms stall would otherwise set the mean of a few calls
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        a.record()
         res = run()
-    e1.record()
+        b.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    per_call = sorted(a.elapsed_time(b) for a, b in evs)
+    ms = per_call[len(per_call) // 2] if len(per_call) % 2 else 0.5 * (per_call[len(per_call) // 2 - 1] +
+                                                                      per_call[len(per_call) // 2])
+    ms_mean, ms_min = sum(per_call) / len(per_call), per_call[0]
     finite = True if res is None else bool(torch.isfinite(res.mean).all().item())
     if world > 1:
         t = torch.tensor([ms, 0.0 if finite else 1.0], dtype=torch.float64, device=dev)
@@ -922,8 +928,9 @@ def run_bearings(args):
                                                                 + " (BASELINE.json configs[4])" if runs > 1
                                                                 else " (BASELINE.json configs[1])"),
                           "n_gpus": world, "parallelism": f"batch-shard x{world} (round-robin, no collective)" if world > 1 else "single GPU",
-                          "ms_per_call": ms, "value": runs * T * n_iter / (ms * 1e-3), "unit": "step-passes/s",
-                          "finite": finite}))
+                          "ms_per_call": ms, "ms_per_call_mean": ms_mean, "ms_per_call_min": ms_min,
+                          "timing": f"median of {args.steps} calls, CUDA events around each call",
+                          "value": runs * T * n_iter / (ms * 1e-3), "unit": "step-passes/s", "finite": finite}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -74,8 +74,16 @@ int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_
   if (T <= 0 || batch <= 0 || chunk_len < 0) return PSQRT_EINVAL;
   long long K = chunk_len;
   if (K == 0) {
-    // sub-warp sweeps (psqrt_coopsweep.cuh): 8 lanes per chunk, two 256-thread CTAs per SM
-    long long per_seq = (ln->coop_mask() ? kTargetThreads / 4 : kTargetThreads) / batch;
+    // sub-warp sweeps (psqrt_coopsweep.cuh): 64 chunks per SM (two CTAs of 32 chunks).  PSQRT_TARGET_CHUNKS overrides
+    // the number of chunks aimed at over the whole batch (tuning runs).
+    static const long long env_target = [] { const char* e = getenv("PSQRT_TARGET_CHUNKS"); return e ? atoll(e) : 0LL; }();
+    // nx = 5: one 128-thread CTA per SM instead of two (its sweeps spill ~1 KB per thread; measured 0.545 -> 0.467 ms
+    // per pass at T = 1e6 and 217 -> 192 us per bearings iteration at T = 1e5; nx = 3, 4, 6 gain nothing from it)
+    const long long target = env_target > 0 ? env_target
+                             : ln->coop_mask() ? kTargetThreads / 4
+                             : ln->n == 5      ? kTargetThreads / 2
+                                               : kTargetThreads;
+    long long per_seq = target / batch;
     if (per_seq < 32) per_seq = 32;
     K = (T + per_seq - 1) / per_seq;
     if (K < kMinChunk) K = kMinChunk;

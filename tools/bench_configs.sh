@@ -10,13 +10,13 @@ $B --nx 8 --ny 4                     2>&1 | tail -1 > gpurun_out/configs_c4_lgss
 $B --nx 8 --ny 4 --T 10000000 --steps 5 2>&1 | tail -1 > gpurun_out/configs_c4_lgssm_n8_T1e7.json
 $B --no-host-model                   2>&1 | tail -1 > gpurun_out/configs_lgssm_n4_T1e6_timevarying_path.json
 for lin in extended cubature gauss_hermite; do
-  python bench.py --workload bearings --lin $lin --steps 5 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c2_bearings_$lin.json
+  python bench.py --workload bearings --lin $lin --steps 9 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c2_bearings_$lin.json
 done
 python bench.py --workload bearings --lin extended --T 10000 --runs 100 --iters 20 --steps 2 --warmup 1 2>&1 | tail -1 > gpurun_out/configs_c5_bearings_100runs_T1e4.json
 python bench.py --workload bearings --lin extended --T 10000 --runs 100 --iters 20 --batched --steps 3 --warmup 1 2>&1 | tail -1 > gpurun_out/configs_c5_bearings_100runs_T1e4_batched.json
-python bench.py --workload bearings --lin unscented --steps 5 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c2_bearings_unscented.json
+python bench.py --workload bearings --lin unscented --steps 9 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c2_bearings_unscented.json
 for lin in extended cubature gauss_hermite; do
-  python bench.py --workload bearings --grad --lin $lin --steps 3 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c3_grad_$lin.json
+  python bench.py --workload bearings --grad --lin $lin --steps 5 --warmup 2 2>&1 | tail -1 > gpurun_out/configs_c3_grad_$lin.json
 done
 python - <<'PY'
 import glob, json
