@@ -739,7 +739,7 @@ def run_psqrt(args):
         secondary["c4_strong"] = res
 
     if rank == 0:
-        plan = _lib.get_plan(NX, NY, T, 1, 0)
+        plan = _lib.get_plan(NX, NY, T, 1, args.chunk, ssm=ssm)
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -90,8 +90,12 @@ int psqrt_version(void);
 const char* psqrt_error_string(int code);
 /* 1 if kernels for (nx, ny) are compiled in; ny = 0 asks about smoother-only support. */
 int psqrt_supported(int nx, int ny);
-/* Chunking used for a problem size; chunk_len = 0 lets the library choose. */
+/* Chunking used for a problem size; chunk_len = 0 lets the library choose.  The library's choice depends on the state
+ * dimension and, for nx <= 4, on whether the TRANSITION part of the model is time-invariant with host mirrors (it then
+ * travels by value and the sweeps want fewer, longer chunks): psqrt_get_plan answers for a model read from device
+ * memory, psqrt_get_plan_ssm for the model given.  Every stage of a pass makes the same choice from the same model. */
 int psqrt_get_plan(int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqrt_plan* out);
+int psqrt_get_plan_ssm(const psqrt_ssm* ssm, int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqrt_plan* out);
 size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, int chunk_len);
 
 /* ---- whole pass: filtering + smoothing (methods.py:38-47 filter_smoother, parallel=True,

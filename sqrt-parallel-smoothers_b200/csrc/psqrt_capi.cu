@@ -64,24 +64,38 @@ const LaunchN* table_for(int nx) {
   }
 }
 
-// Chunking: aim at kTargetThreads resident threads over the whole batch (148 SMs x 256
-// threads, the register-limited occupancy of the sweeps), never fewer than kMinChunk steps per
-// thread so the per-chunk prologue (two applies + one warp scan) stays amortised.
+// Chunking: aim at a number of chunks over the whole batch that depends on the form of the sweeps (make_plan below;
+// kTargetThreads = 148 SMs x 256 threads is the register-limited occupancy of the per-thread sweeps), never fewer than
+// kMinChunk steps per thread so the per-chunk prologue (two applies + one warp scan) stays amortised.
 constexpr long long kTargetThreads = 148LL * 256;
 constexpr int kMinChunk = 4;
 
-int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, psqrt_plan* p) {
+// Which chunk-count target a pass uses must be the same in every stage of the pass (they share the scratch layouts),
+// so it may depend only on what every stage sees: the state dimension and the TRANSITION part of the model.
+// one_cta: per-thread sweeps with ONE 128-thread CTA per SM, three SMs left over (145 x 128 chunks), instead of two CTAs
+// per SM (148 x 256).  The step loops are bound by FP64 issue and run no faster with two CTAs, which only double the
+// chunk prologues and the mid-scan input; a grid that fills all 148 SMs exactly is slower again.  Measured on B200
+// (T = 1e6, nx = 4, model by value: K = 27 / 53 / 54 -> 0.2669 / 0.2676 / 0.2646 ms per pass; nx = 5: 0.545 -> 0.471 ms;
+// T = 1e5: nx = 4 0.115 -> 0.098, nx = 5 0.202 -> 0.165 ms).  A model read from HBM per step (nx <= 4, T = 1e6:
+// 0.292 ms with two CTAs, 0.336 with one) needs the second CTA to hide its loads; nx = 6 keeps two as well.
+bool one_cta_plan(const LaunchN* ln, const psqrt_ssm* s) {
+  if (ln->coop_mask()) return false;
+  if (ln->n == 5) return true;
+  if (ln->n > 5 || !s) return false;
+  return s->fused_model == PSQRT_FUSED_NONE && s->hF && s->hcholQ && s->hb && !s->F_ts && !s->cholQ_ts && !s->b_ts &&
+         !s->F_bs && !s->cholQ_bs && !s->b_bs;
+}
+
+int make_plan(const LaunchN* ln, int64_t T, int64_t batch, int chunk_len, bool one_cta, psqrt_plan* p) {
   if (T <= 0 || batch <= 0 || chunk_len < 0) return PSQRT_EINVAL;
   long long K = chunk_len;
   if (K == 0) {
     // sub-warp sweeps (psqrt_coopsweep.cuh): 64 chunks per SM (two CTAs of 32 chunks).  PSQRT_TARGET_CHUNKS overrides
     // the number of chunks aimed at over the whole batch (tuning runs).
     static const long long env_target = [] { const char* e = getenv("PSQRT_TARGET_CHUNKS"); return e ? atoll(e) : 0LL; }();
-    // nx = 5: one 128-thread CTA per SM instead of two (its sweeps spill ~1 KB per thread; measured 0.545 -> 0.467 ms
-    // per pass at T = 1e6 and 217 -> 192 us per bearings iteration at T = 1e5; nx = 3, 4, 6 gain nothing from it)
     const long long target = env_target > 0 ? env_target
                              : ln->coop_mask() ? kTargetThreads / 4
-                             : ln->n == 5      ? kTargetThreads / 2
+                             : one_cta         ? 145LL * 128
                                                : kTargetThreads;
     long long per_seq = target / batch;
     if (per_seq < 32) per_seq = 32;
@@ -235,7 +249,8 @@ struct Ctx {
   Ws ws;
 };
 
-int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws, size_t ws_bytes) {
+int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws, size_t ws_bytes,
+          const psqrt_ssm* ssm) {
   c.ln = table_for(nx);
   if (!c.ln) return PSQRT_EUNSUPPORTED;
   c.lny = nullptr;
@@ -244,7 +259,7 @@ int setup(Ctx& c, int nx, int ny, int64_t T, int64_t B, int chunk_len, void* ws,
     if (!c.lny) return PSQRT_EUNSUPPORTED;
   }
   if (B > 65535) return PSQRT_EINVAL;
-  int rc = make_plan(c.ln, T, B, chunk_len, &c.plan);
+  int rc = make_plan(c.ln, T, B, chunk_len, one_cta_plan(c.ln, ssm), &c.plan);
   if (rc) return rc;
   c.ws = carve(ws, c.plan, c.ln->nf_state, B, T);
   if (!ws || ws_bytes < c.ws.doubles * sizeof(double)) return PSQRT_EWORKSPACE;
@@ -280,16 +295,28 @@ int psqrt_get_plan(int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqr
   const LaunchN* ln = table_for(nx);
   if (!ln) return PSQRT_EUNSUPPORTED;
   if (!out) return PSQRT_EINVAL;
-  return make_plan(ln, T, batch, chunk_len, out);
+  return make_plan(ln, T, batch, chunk_len, one_cta_plan(ln, nullptr), out);
+}
+
+int psqrt_get_plan_ssm(const psqrt_ssm* ssm, int nx, int ny, int64_t T, int64_t batch, int chunk_len, psqrt_plan* out) {
+  const LaunchN* ln = table_for(nx);
+  if (!ln || (ny > 0 && !ln->for_ny(ny))) return PSQRT_EUNSUPPORTED;
+  if (!out) return PSQRT_EINVAL;
+  return make_plan(ln, T, batch, chunk_len, one_cta_plan(ln, ssm), out);
 }
 
 size_t psqrt_workspace_bytes(int op, int nx, int ny, int64_t T, int64_t batch, int chunk_len) {
   const size_t gen = (op == PSQRT_OP_FILTER_SMOOTHER) ? psqrt_generic_workspace_bytes(nx, T, batch, 0) : 0;
   if (!tuned_dims(nx, ny)) return gen;   // served by the generic path (0 if it cannot either)
   const LaunchN* ln = table_for(nx);
-  psqrt_plan p;
-  if (make_plan(ln, T, batch, chunk_len, &p)) return 0;
-  const size_t tuned = carve(nullptr, p, ln->nf_state, batch, T).doubles * sizeof(double);
+  // the plan may depend on the form of the model (one_cta_plan): a workspace of this size serves either
+  size_t tuned = 0;
+  for (int v = 0; v < 2; ++v) {
+    psqrt_plan p;
+    if (make_plan(ln, T, batch, chunk_len, v != 0, &p)) return 0;
+    const size_t b = carve(nullptr, p, ln->nf_state, batch, T).doubles * sizeof(double);
+    tuned = b > tuned ? b : tuned;
+  }
   return (force_generic() && gen > tuned) ? gen : tuned;
 }
 
@@ -299,7 +326,7 @@ int psqrt_filter_reduce(const psqrt_ssm* ssm, const double* y, int nx, int ny, i
   if (!ssm_ok(ssm, true, nx, ny) || !y || ny <= 0) return PSQRT_EINVAL;
   if (peer && !peer_ok(peer, batch)) return PSQRT_EINVAL;
   Ctx c;
-  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes, ssm);
   if (rc) return rc;
   if (peer && peer->payload != c.ln->nf_filter) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -342,7 +369,7 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   if (!ssm_ok(ssm, true, nx, ny) || !y || ny <= 0 || !carry_m || !carry_L || !fm || !fL) return PSQRT_EINVAL;
   if (peer && (!peer_ok(peer, batch) || !stotal)) return PSQRT_EINVAL;
   Ctx c;
-  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes, ssm);
   if (rc) return rc;
   if (peer && peer->payload != c.ln->nf_smoother + nx + (int64_t)nx * nx) return PSQRT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -421,7 +448,7 @@ int psqrt_smoother_apply(const psqrt_ssm* ssm, const double* fm, const double* f
   // the sub-warp form (nx = 6, 8) reads the trajectory itself
   if (!ssm_ok(ssm, false, nx, 0) || !carry_m || !carry_L || !sm || !sL) return PSQRT_EINVAL;
   Ctx c;
-  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes, ssm);
   if (rc) return rc;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
   bind_fused(a, c.ws, T);
@@ -439,7 +466,7 @@ int psqrt_filter_smoother(const psqrt_ssm* ssm, const double* y, const double* m
   if ((!tuned_dims(nx, ny) || force_generic()) && ssm && ssm->fused_model == PSQRT_FUSED_NONE)
     return psqrt_filter_smoother_generic(ssm, y, m0, L0, nx, ny, T, batch, fm, fL, sm, sL, ell, ws, ws_bytes, stream);
   Ctx c;
-  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, ny, T, batch, chunk_len, ws, ws_bytes, ssm);
   if (rc) return rc;
   rc = psqrt_filter_reduce(ssm, y, nx, ny, T, batch, chunk_len, c.ws.ftotal, ws, ws_bytes, nullptr, stream);
   if (rc) return rc;
@@ -465,7 +492,7 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
     return psqrt_filter_smoother_generic(ssm, nullptr, nullptr, nullptr, nx, 0, T, batch, const_cast<double*>(fm),
                                          const_cast<double*>(fL), sm, sL, nullptr, ws, ws_bytes, stream);
   Ctx c;
-  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes, ssm);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   SSMArgs a = make_args(ssm, nullptr, 0, T);
@@ -498,7 +525,7 @@ int psqrt_filter_scan(const double* A, const double* b, const double* U, const d
                       size_t ws_bytes, void* stream) {
   if (!A || !b || !U || !eta || !Z || !means || !chols) return PSQRT_EINVAL;
   Ctx c;
-  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, 0, T, batch, chunk_len, ws, ws_bytes, nullptr);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c.ln->escan_filter_reduce(A, b, U, eta, Z, T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_pref,
@@ -522,7 +549,7 @@ int psqrt_smoother_scan(const double* g, const double* E, const double* D, int n
                         int chunk_len, double* means, double* chols, void* ws, size_t ws_bytes, void* stream) {
   if (!g || !E || !D || !means || !chols) return PSQRT_EINVAL;
   Ctx c;
-  int rc = setup(c, nx, 0, n, batch, chunk_len, ws, ws_bytes);
+  int rc = setup(c, nx, 0, n, batch, chunk_len, ws, ws_bytes, nullptr);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c.ln->escan_smooth_reduce(g, E, D, n, c.plan.chunk_len, c.plan.n_chunks_pad, batch, c.ws.chunk_suf, c.ws.warp_stot,

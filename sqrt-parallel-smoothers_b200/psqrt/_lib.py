@@ -55,7 +55,8 @@ class Plan(ctypes.Structure):
 
 
 EXPORTS = (
-    "psqrt_version", "psqrt_error_string", "psqrt_supported", "psqrt_get_plan", "psqrt_workspace_bytes",
+    "psqrt_version", "psqrt_error_string", "psqrt_supported", "psqrt_get_plan", "psqrt_get_plan_ssm",
+    "psqrt_workspace_bytes",
     "psqrt_filter_smoother", "psqrt_smoother", "psqrt_filter_reduce", "psqrt_carry_filter", "psqrt_filter_apply",
     "psqrt_carry_smoother", "psqrt_smoother_apply", "psqrt_filter_elements", "psqrt_filter_scan",
     "psqrt_smoother_elements", "psqrt_smoother_scan", "psqrt_loglik_terms", "psqrt_filter_combine",
@@ -168,9 +169,18 @@ def supported(nx: int, ny: int = 0) -> bool:
     return bool(load().psqrt_supported(int(nx), int(ny)))
 
 
-def get_plan(nx: int, ny: int, T: int, batch: int = 1, chunk_len: int = 0) -> Plan:
+def get_plan(nx: int, ny: int, T: int, batch: int = 1, chunk_len: int = 0, ssm: "Optional[LinearizedSSM]" = None) -> Plan:
+    """The chunking the library uses; with `ssm`, the one it uses for that model (psqrt_get_plan_ssm: a time-invariant
+    transition model carried by value gets fewer, longer chunks at nx <= 4)."""
     p = Plan()
-    _check(load().psqrt_get_plan(nx, ny, T, batch, chunk_len, ctypes.byref(p)), "psqrt_get_plan")
+    lib = load()
+    if ssm is None:
+        _check(lib.psqrt_get_plan(nx, ny, T, batch, chunk_len, ctypes.byref(p)), "psqrt_get_plan")
+    else:
+        keep = []
+        s = ssm.struct(T, batch, keep)
+        _check(lib.psqrt_get_plan_ssm(ctypes.byref(s), nx, ny, ctypes.c_int64(T), ctypes.c_int64(batch), chunk_len,
+                                      ctypes.byref(p)), "psqrt_get_plan_ssm")
     return p
 
 

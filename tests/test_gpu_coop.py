@@ -116,3 +116,40 @@ def test_full_size_nx8_properties():
     ofm, ofc, _, _, _ = oracle_from_ssm(pre)
     assert rel_err(fm[:Tc + 1].cpu().numpy(), ofm) < 1e-9
     assert rel_err(LLt(fL[:Tc + 1].cpu().numpy()), LLt(ofc)) < 1e-9
+
+
+@pytest.mark.parametrize("n,ny,T", [(4, 2, 200000), (3, 1, 150000), (5, 2, 20000), (4, 2, 3000)])
+def test_plan_follows_the_transition_model_only(n, ny, T):
+    """The chunk plan of a pass depends on the state dimension and on the form of the TRANSITION model (by value or read
+    from memory: psqrt_get_plan_ssm), never on the observation part, so that every stage of a pass -- the backward sweep
+    sees no observation model -- cuts the sequence the same way.  Host mirrors for the transition part only: forward
+    sweeps read the model from memory, the backward sweep takes it by value, same plan; all three forms of the model
+    give the same pass (association order differs: 1e-10) and agree with the oracle on a prefix."""
+    from psqrt import _lib
+    case = lgssm_case(n, ny, T, seed=17 * n + ny)
+    names = ("F", "cholQ", "b", "H", "cholR", "c")
+    dev_arrays = [_g(case[k]) for k in names]
+    full = _lib.LinearizedSSM(*dev_arrays, host={k: case[k] for k in names})
+    part = _lib.LinearizedSSM(*dev_arrays, host={k: case[k] for k in names[:3]})
+    none = _lib.LinearizedSSM(*dev_arrays)
+    p_full, p_part, p_none = (_lib.get_plan(n, ny, T, 1, 0, ssm=s) for s in (full, part, none))
+    assert p_full.chunk_len == p_part.chunk_len
+    assert p_none.chunk_len <= p_full.chunk_len
+    if n <= 4 and T >= 100000:
+        assert p_none.chunk_len < p_full.chunk_len           # a model read from memory gets more, shorter chunks
+    assert _lib.get_plan(n, ny, T).chunk_len == p_none.chunk_len
+    outs = [_lib.filter_smoother(ssm, _g(case["ys"]), _g(case["m0"]), _g(case["L0"]), smooth=True, loglik=True)
+            for ssm in (full, part, none)]
+    for o in outs[1:]:
+        assert rel_err(o[0].cpu().numpy(), outs[0][0].cpu().numpy()) < 1e-10
+        assert rel_err(o[2].cpu().numpy(), outs[0][2].cpu().numpy()) < 1e-10
+        assert rel_err(LLt(o[3][::53].cpu().numpy()), LLt(outs[0][3][::53].cpu().numpy())) < 1e-10
+        assert abs(o[4].item() - outs[0][4].item()) <= 1e-10 * abs(outs[0][4].item())
+    Tc = min(T, 3000)
+    pre = {k: (v[:Tc] if k == "ys" else v) for k, v in case.items()}
+    ofm, ofc, osm, osc, _ = oracle_from_ssm(pre)
+    assert rel_err(outs[0][0][:Tc + 1].cpu().numpy(), ofm) < 1e-9
+    assert rel_err(LLt(outs[0][1][:Tc + 1].cpu().numpy()), LLt(ofc)) < 1e-9
+    if Tc == T:
+        assert rel_err(outs[0][2].cpu().numpy(), osm) < 1e-9
+        assert rel_err(LLt(outs[0][3].cpu().numpy()), LLt(osc)) < 1e-9
