@@ -153,3 +153,13 @@ def test_plan_follows_the_transition_model_only(n, ny, T):
     if Tc == T:
         assert rel_err(outs[0][2].cpu().numpy(), osm) < 1e-9
         assert rel_err(LLt(outs[0][3].cpu().numpy()), LLt(osc)) < 1e-9
+
+
+def test_random_configurations():
+    """tools/fuzz_coop.py: 40 random (nx, ny, T, chunk length, time-varying / by-value model, smoother on / off) passes
+    against the oracle (nx = 8 on the sub-warp sweeps, nx <= 6 per thread with the current chunk plans)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_coop.py"), "40", "7"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = [ln for ln in r.stdout.splitlines() if ln.startswith("WORST")]
+    assert worst and float(worst[-1].split()[1]) < 1e-9, r.stdout[-3000:]
