@@ -763,7 +763,10 @@ def run_psqrt(args):
             "e2e": e2e,
             # K1, K2, K3 (the smoothing mid scan K4 runs inside it on spare CTAs unless PSQRT_FUSE_MID=0), K5;
             # time-sharded with the peer exchange: + K4 and the two carry scans
-            "gpu_launches": ((4 if os.environ.get("PSQRT_FUSE_MID", "1") != "0" else 5) if world == 1 else 7) * args.steps,
+            # kernels of one pass: K1, K2, K3 (+ K4 inside unless PSQRT_FUSE_MID=0; the nx = 8 sub-warp form has its own
+            # launch list), K5; a time-sharded pass adds the two carry kernels
+            "gpu_launches": ((4 if os.environ.get("PSQRT_FUSE_MID", "1") != "0" else 5) + (0 if world == 1 else 2))
+                            * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         if parity is not None:

@@ -130,11 +130,15 @@ int psqrt_smoother(const psqrt_ssm* ssm, const double* fm, const double* fL, int
  * (peer != NULL; NVLink / NVSwitch P2P, e.g. CUDA IPC or torch symmetric memory):
  *   - every rank owns ONE exchange buffer of psqrt_peer_layout(...) 8-byte words, zeroed once, mapped into all
  *     ranks; `bufs` is a DEVICE array of the n_ranks base pointers as seen from this rank;
- *   - the CTA that finishes the mid-level scan of psqrt_filter_reduce (psqrt_filter_apply) stores the shard total
- *     (and, for the smoother phase, the shard's last filtered state) straight into slot `rank` of EVERY rank's
- *     buffer, then publishes the pass number there;
- *   - psqrt_carry_filter (psqrt_carry_smoother) waits, on the GPU and in stream order, until ALL ranks have
- *     published that pass number and folds the totals it needs out of its local buffer (totals / mT / LT ignored).
+ *   - filter phase: the CTA that finishes the mid-level scan of psqrt_filter_reduce stores the shard total straight
+ *     into slot `rank` of EVERY rank's buffer, then publishes the pass number there; psqrt_carry_filter waits, on the
+ *     GPU and in stream order, until ALL ranks have published that pass number and folds the totals it needs out of
+ *     its local buffer (totals ignored);
+ *   - smoother phase: psqrt_filter_apply only WRITES the shard's smoothing total (stotal; its `peer` argument is
+ *     validated, nothing is sent -- the total may then come from the scan hidden inside the forward sweep);
+ *     psqrt_carry_smoother is given this rank's OWN total (totals = stotal [B, nf_smoother]) and last filtered state
+ *     (mT, LT = fm[:, T], fL[:, T]), publishes them in every rank's buffer, waits for all ranks and folds the totals of
+ *     the later shards onto the last rank's published state.
  * Pass numbers are counted on the device (one counter per sequence and phase) and the slots are double-buffered by
  * pass parity: no per-pass host argument (a whole time-sharded pass replays from one CUDA graph), nothing is ever
  * reset, and -- because every carry waits for all ranks -- no rank can run more than one pass ahead of a reader of

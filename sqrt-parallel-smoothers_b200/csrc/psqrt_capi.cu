@@ -380,7 +380,7 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   // Without a peer exchange and for a single sequence the smoothing mid scan (K4) runs inside K3 on a few extra
   // CTAs, concurrently with the workers' step loops (psqrt_kernels.cuh, fused_smooth_mid); PSQRT_FUSE_MID=0: own kernel.
   static const bool fuse_env = [] { const char* e = getenv("PSQRT_FUSE_MID"); return e ? atoi(e) != 0 : true; }();
-  const bool fuse = smooth && !peer && batch == 1 && fuse_env && !(c.ln->coop_mask() & 2);
+  const bool fuse = smooth && batch == 1 && fuse_env && !(c.ln->coop_mask() & 2);
   psq::FuseArgs fa;
   fa.group_s = c.ws.group_s; fa.stotal = stotal; fa.ctr = fuse ? c.ws.counter_x : nullptr;
   c.lny->filter_apply(smooth, a, host_model(ssm, true, &hmv), T, c.plan.chunk_len, c.plan.n_chunks_pad, batch, carry_m,
@@ -389,16 +389,10 @@ int psqrt_filter_apply(const psqrt_ssm* ssm, const double* y, const double* carr
   if (fuse) {
     if (ell) psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
   } else if (smooth) {
-    psq::PushArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    if (peer) {
-      // the smoothing total travels with the shard's last filtered state (the last rank's is the terminal element)
-      pa.pc = peer_ctx(peer); pa.on = 1;
-      pa.x1 = fm + (size_t)T * nx; pa.s1 = (long long)(T + 1) * nx; pa.n1 = nx;
-      pa.x2 = fL + (size_t)T * nx * nx; pa.s2 = (long long)(T + 1) * nx * nx; pa.n2 = nx * nx;
-    }
+    // time-sharded pass: the smoothing total is published -- together with the shard's last filtered state -- by
+    // psqrt_carry_smoother, so that it may come from the scan hidden inside K3 as well as from this kernel
     c.ln->mid_smooth(c.ws.warp_stot, c.plan.n_warps, batch, c.ws.group_s, c.ws.counter_s, stotal,
-                     ell ? c.ws.ell_part : nullptr, ell, peer ? &pa : nullptr, st);
+                     ell ? c.ws.ell_part : nullptr, ell, nullptr, st);
   } else if (ell) {
     psq::ell_sum(c.ws.ell_part, c.plan.n_warps, batch, ell, st);
   }
@@ -415,6 +409,7 @@ int psqrt_carry_smoother(const double* totals, int rank, int n_ranks, int64_t ba
     if (!peer_ok(peer, batch) || peer->rank != rank || peer->n_ranks != n_ranks ||
         peer->payload != ln->nf_smoother + nx + (int64_t)nx * nx)
       return PSQRT_EINVAL;
+    if (!totals || !mT || !LT) return PSQRT_EINVAL;   // this rank's own total and last filtered state: published here
     pc = peer_ctx(peer);
   } else if (!mT || !LT || (rank + 1 < n_ranks && !totals)) {
     return PSQRT_EINVAL;

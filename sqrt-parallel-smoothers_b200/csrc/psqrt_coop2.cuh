@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kCarryIT * OP::G, 1)
 k_carry_scan(const double* __restrict__ totals, int first, int step, int count, long long B, long long payload,
              const double* __restrict__ m, const double* __restrict__ L, long long ms, long long Ls,
              double* __restrict__ cm, double* __restrict__ cL, const PeerCtx pc, int use_peer, int seed_rank,
-             long long mext, long long Lext) {
+             long long mext, long long Lext, const PushArgs push, const double* __restrict__ own_total) {
   constexpr int G = OP::G;
   constexpr int NFD = OP::NFD;
   constexpr int IT = kCarryIT;
@@ -677,6 +677,42 @@ k_carry_scan(const double* __restrict__ totals, int first, int step, int count, 
   for (int f = threadIdx.x; f < NF; f += blockDim.x) dmap[f] = OP::dense_of(f);
   for (int k = threadIdx.x; k < 2 * IT * NFD; k += blockDim.x) slots[k] = 0.0;
   if (use_peer) {
+    if (push.on) {
+      // Deferred publication: this rank's own total (own_total [B][NF]) and extras go into every rank's buffer HERE,
+      // by the consumer, instead of by the kernel that produced them -- which lets the producer be the smoothing mid
+      // scan hidden inside K3 (fused_smooth_mid), whose extras (the shard's last filtered state) exist only when K3
+      // has ended.  Same protocol as the push of k_mid_scan2 / k_mid_scan3.
+      if (x == 0) {
+        const PeerCtx& pp = push.pc;
+        const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+        unsigned long long ep = 0;
+        if (l == 0) {
+          volatile unsigned long long* c =
+              reinterpret_cast<volatile unsigned long long*>(pp.bufs[pp.rank] + pp.ctr_off + seq);
+          ep = *c + 1ull;
+          *c = ep;
+        }
+        ep = __shfl_sync(gmask, ep, gbase);
+        const long long off = pp.data_off + (long long)(ep & 1ull) * pp.n_ranks * pp.slot + (long long)pp.rank * pp.slot +
+                              seq * pp.payload;
+        for (int r = 0; r < pp.n_ranks; ++r) {
+          double* dst = pp.bufs[r] + off;
+          for (int f = l; f < NF; f += G) dst[f] = own_total[seq * NF + f];
+          for (int k = l; k < push.n1; k += G) dst[NF + k] = push.x1[seq * push.s1 + k];
+          for (int k = l; k < push.n2; k += G) dst[NF + push.n1 + k] = push.x2[seq * push.s2 + k];
+        }
+        __threadfence_system();
+        __syncwarp(gmask);
+        if (l == 0) {
+          for (int r = 0; r < pp.n_ranks; ++r) {
+            volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
+                pp.bufs[r] + pp.flags_off + (long long)pp.rank * pp.batch + seq);
+            *f = ep;
+          }
+        }
+      }
+      __syncthreads();
+    }
     // every rank has published pass number `epoch` for this sequence (all ranks, not only the ones whose totals
     // are folded: this is the back-edge that keeps any rank from running two passes ahead of a reader)
     const double* mine = pc.bufs[pc.rank];

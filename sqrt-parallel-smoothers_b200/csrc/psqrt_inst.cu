@@ -454,7 +454,7 @@ void mid_smooth(double* items, long long M, long long B, double* groups, unsigne
 template <class OP, int NF>
 void launch_carry(const double* totals, int first, int step, int count, long long B, const double* m, const double* L,
                   double* cm, double* cL, const PeerCtx* pc, int seed_rank, long long mext, long long Lext,
-                  cudaStream_t st) {
+                  const PushArgs* push, const double* own_total, cudaStream_t st) {
   constexpr size_t smem = carry_smem_bytes<OP, NF>();
   static_assert(smem <= 227 * 1024, "carry scan: shared memory budget");
   auto kern = k_carry_scan<OP, NF, N>;
@@ -462,18 +462,33 @@ void launch_carry(const double* totals, int first, int step, int count, long lon
   PeerCtx p;
   if (pc) p = *pc; else memset(&p, 0, sizeof(p));
   const long long payload = pc ? pc->payload : NF;
+  PushArgs pa;
+  if (push) pa = *push; else memset(&pa, 0, sizeof(pa));
   kern<<<(unsigned)B, kCarryIT * OP::G, smem, st>>>(totals, first, step, count, B, payload, m, L, (long long)N,
-                                                    (long long)N * N, cm, cL, p, pc ? 1 : 0, seed_rank, mext, Lext);
+                                                    (long long)N * N, cm, cL, p, pc ? 1 : 0, seed_rank, mext, Lext, pa,
+                                                    own_total);
 }
 void carry_filter(const double* totals, int rank, long long B, const double* m0, const double* L0, double* cm,
                   double* cL, const PeerCtx* pc, cudaStream_t st) {
-  launch_carry<CoopF2<N>, FElem<N>::NF>(totals, 0, 1, rank, B, m0, L0, cm, cL, pc, -1, 0, 0, st);
+  launch_carry<CoopF2<N>, FElem<N>::NF>(totals, 0, 1, rank, B, m0, L0, cm, cL, pc, -1, 0, 0, nullptr, nullptr, st);
 }
 void carry_smoother(const double* totals, int rank, int R, long long B, const double* mT, const double* LT,
                     double* cm, double* cL, const PeerCtx* pc, cudaStream_t st) {
-  // with a peer exchange the terminal state is the last rank's published last filtered state
-  launch_carry<CoopS2<N>, SElem<N>::NF>(totals, R - 1, -1, R - 1 - rank, B, mT, LT, cm, cL, pc, pc ? R - 1 : -1,
-                                        SElem<N>::NF, SElem<N>::NF + N, st);
+  // With a peer exchange `totals` [B][NF] is this rank's OWN smoothing total and (mT, LT) its own last filtered
+  // state: the kernel publishes them to every rank first, then waits for all ranks; the terminal state is the last
+  // rank's published last filtered state.
+  if (pc) {
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.pc = *pc; pa.on = 1;
+    pa.x1 = mT; pa.s1 = N; pa.n1 = N;
+    pa.x2 = LT; pa.s2 = (long long)N * N; pa.n2 = N * N;
+    launch_carry<CoopS2<N>, SElem<N>::NF>(nullptr, R - 1, -1, R - 1 - rank, B, mT, LT, cm, cL, pc, R - 1, SElem<N>::NF,
+                                          SElem<N>::NF + N, &pa, totals, st);
+    return;
+  }
+  launch_carry<CoopS2<N>, SElem<N>::NF>(totals, R - 1, -1, R - 1 - rank, B, mT, LT, cm, cL, nullptr, -1, SElem<N>::NF,
+                                        SElem<N>::NF + N, nullptr, nullptr, st);
 }
 #else
 inline dim3 mid_grid(long long M, long long B) { return dim3((unsigned)((M + 31) / 32), (unsigned)B, 1); }

@@ -436,7 +436,9 @@ def filter_apply(ssm, y, carry_m, carry_L, *, smooth=True, loglik=False, chunk_l
 
 
 def carry_smoother(totals, rank, n_ranks, mT, LT, peer=None):
-    """With `peer`, totals / mT / LT are only templates for the output shapes (the kernel reads the exchange buffer)."""
+    """Without `peer`: totals [R, B, nf] all-gathered smoothing totals, (mT, LT) the last rank's last filtered state.
+    With `peer`: totals [B, nf] is THIS rank's smoothing total and (mT, LT) its own last filtered state; the kernel
+    publishes them in every rank's exchange buffer, waits for all ranks and folds the later shards' totals."""
     lib = load()
     B, nx = mT.shape
     cm, cL = torch.empty_like(mT), torch.empty_like(LT)

@@ -148,7 +148,9 @@ class TimeShardedSmoother:
             return fm, fL, None, None, ell
         nfs = stotal.shape[-1]
         if peer is not None:
-            sm_c, sL_c = ops.carry_smoother(None, r, R, m0, L0, peer=peer.smoother_phase)   # m0 / L0: shape templates
+            # the carry kernel publishes this shard's smoothing total and last filtered state, waits for all ranks, folds
+            sm_c, sL_c = ops.carry_smoother(stotal, r, R, fm[:, -1].contiguous(), fL[:, -1].contiguous(),
+                                            peer=peer.smoother_phase)
         else:
             payload = torch.cat([stotal, fm[:, -1], fL[:, -1].reshape(B, -1)], dim=-1)       # [B, nfs + nx + nx^2]
             gathered = _all_gather(payload, R, self.group)
