@@ -240,6 +240,54 @@ struct CoopModelR {
   }
 };
 
+// K1 only: where the model of a step is read from.  A time-invariant part is staged ONCE per CTA in a shared-memory
+// bank; a time-varying part is read from global memory at its step.  Either way the rows are loaded where they are
+// used -- nothing of the model stays in registers across the step loop, which K1 (five state matrices per lane) needs
+// for its triangularisations: stack 600 -> 112 bytes, 1.12 -> 1.03 ms at T = 1e6.  K3 and K5 keep the model rows in
+// registers (CoopModelR): loading at the point of use made them 7 - 10 % slower.
+template <int N, int NY>
+struct CoopBank {
+  static constexpr int bF = 0, bQ = N * N, bb = 2 * N * N, bH = 2 * N * N + N, bR = bH + NY * N, bc = bR + NY * NY;
+  static constexpr int SZ = (bc + NY + 1) & ~1;
+  const double *F, *Q, *bq, *H, *R, *c;   // this step's model (generic addresses: bank or global)
+  bool vt, vo;                            // 16-byte loads allowed for the transition / observation rows
+  // all threads of the CTA; followed by __syncthreads() in the caller
+  static __device__ __forceinline__ void fill(double* bank, const SSMArgs& a, long long seq, bool tv_t, bool tv_o,
+                                              bool obs) {
+    if (!tv_t) {
+      for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+        bank[bF + i] = a.F[seq * a.sF + i];
+        bank[bQ + i] = a.Q[seq * a.sQ + i];
+      }
+      for (int i = threadIdx.x; i < N; i += blockDim.x) bank[bb + i] = a.bq[seq * a.sb + i];
+    }
+    if (obs && !tv_o) {
+      for (int i = threadIdx.x; i < NY * N; i += blockDim.x) bank[bH + i] = a.H[seq * a.sH + i];
+      for (int i = threadIdx.x; i < NY * NY; i += blockDim.x) bank[bR + i] = a.R[seq * a.sR + i];
+      for (int i = threadIdx.x; i < NY; i += blockDim.x) bank[bc + i] = a.c[seq * a.sc + i];
+    }
+  }
+  __device__ __forceinline__ void at(const double* bank, const SSMArgs& a, long long seq, long long k, bool tv_t,
+                                     bool tv_o, bool obs, bool vec) {
+    F = tv_t ? a.F + seq * a.sF + k * a.tF : bank + bF;
+    Q = tv_t ? a.Q + seq * a.sQ + k * a.tQ : bank + bQ;
+    bq = tv_t ? a.bq + seq * a.sb + k * a.tb : bank + bb;
+    vt = tv_t ? vec : true;
+    if (obs) {
+      H = tv_o ? a.H + seq * a.sH + k * a.tH : bank + bH;
+      R = tv_o ? a.R + seq * a.sR + k * a.tR : bank + bR;
+      c = tv_o ? a.c + seq * a.sc + k * a.tc : bank + bc;
+      vo = tv_o ? vec : (NY * N % 2 == 0);
+    }
+  }
+};
+
+// dynamic shared memory of K1: the 32 group buffers + the model bank
+template <int N, int NY>
+constexpr size_t coopr_k1_smem_bytes() {
+  return CoopSweep<N>::smem_bytes() + sizeof(double) * CoopBank<N, NY>::SZ;
+}
+
 #ifndef PSQ_COOPR_MINB_K1
 #define PSQ_COOPR_MINB_K1 2
 #endif
@@ -620,14 +668,18 @@ k_coopr_filter_reduce(const SSMArgs a, long long T, int K, long long Ppad, doubl
   }
   double* const own = chunk_own + seq * NF * Ppad + c;
   const bool tv_t = (a.tF | a.tQ | a.tb) != 0, tv_o = (a.tH | a.tR | a.tc) != 0;
-  CoopModelR<N, NY, G, R> md;
+  double* const bank = coop_sm + kCChunks * CS::SZ;
+  CoopBank<N, NY>::fill(bank, a, seq, tv_t, tv_o, true);
+  __syncthreads();
+  CoopBank<N, NY> md;
+  const bool hl = l < NY;
+  const int la = hl ? l : 0;
 #pragma unroll 1
   for (int j = 0; j < K; ++j) {
     const bool act = j < len;
     const long long k = act ? k0 + j : 0;
-    if (j == 0 || tv_t) md.load_transition(a, seq, k, l, vec);
-    if (j == 0 || tv_o) md.load_observation(a, seq, k, l, vec);
-    const double yv = (l < NY) ? a.y[seq * a.sy + k * a.ty + l] : 0.0;
+    md.at(bank, a, seq, k, tv_t, tv_o, true, vec);
+    const double yv = hl ? a.y[seq * a.sy + k * a.ty + l] : 0.0;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
       const int rs = l + s * G;
@@ -635,39 +687,45 @@ k_coopr_filter_reduce(const SSMArgs a, long long T, int K, long long Ppad, doubl
       st_row<N>(buf + CS::R1 + rs * RS, A[s]);
       buf[CS::V0 + rs] = b[s];
     }
-    if (l < NY) st_row<N>(buf + CS::HB + l * RS, md.H);
     __syncwarp();
     double M1[R][2 * N], FA[R][N], mp[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) {
-      mp[s] = md.bq[s];
-#pragma unroll
-      for (int q = 0; q < N; ++q) {
-        M1[s][q] = 0.0;
-        FA[s][q] = 0.0;
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < N; ++kk) {
-      double t[N], u[N];
-      ld_row<N>(buf + CS::R0 + kk * RS, t);
-      ld_row<N>(buf + CS::R1 + kk * RS, u);
-      const double bk = buf[CS::V0 + kk];
+    {
+      double Fr[R][N];
 #pragma unroll
       for (int s = 0; s < R; ++s) {
-        const double f = md.F[s][kk];
+        gld_row<N>(md.F + (l + s * G) * N, Fr[s], md.vt);
+        mp[s] = md.bq[l + s * G];
 #pragma unroll
         for (int q = 0; q < N; ++q) {
-          M1[s][q] = fma(f, t[q], M1[s][q]);
-          FA[s][q] = fma(f, u[q], FA[s][q]);
+          M1[s][q] = 0.0;
+          FA[s][q] = 0.0;
         }
-        mp[s] = fma(f, bk, mp[s]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < N; ++kk) {
+        double t[N], u[N];
+        ld_row<N>(buf + CS::R0 + kk * RS, t);
+        ld_row<N>(buf + CS::R1 + kk * RS, u);
+        const double bk = buf[CS::V0 + kk];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          const double f = Fr[s][kk];
+#pragma unroll
+          for (int q = 0; q < N; ++q) {
+            M1[s][q] = fma(f, t[q], M1[s][q]);
+            FA[s][q] = fma(f, u[q], FA[s][q]);
+          }
+          mp[s] = fma(f, bk, mp[s]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        double Qr[N];
+        gld_row<N>(md.Q + (l + s * G) * N, Qr, md.vt);
+#pragma unroll
+        for (int q = 0; q < N; ++q) M1[s][N + q] = (q <= l + s * G) ? Qr[q] : 0.0;
       }
     }
-#pragma unroll
-    for (int s = 0; s < R; ++s)
-#pragma unroll
-      for (int q = 0; q < N; ++q) M1[s][N + q] = (q <= l + s * G) ? md.Q[s][q] : 0.0;
     __syncwarp();
     coop_house_rows<2 * N, N, N, G, R>(M1, l, gbase);
     double Np[R][N];
@@ -694,30 +752,37 @@ k_coopr_filter_reduce(const SSMArgs a, long long T, int K, long long Ppad, doubl
     }
     __syncwarp();
     double hrow[N + NY], mrow[R][N + NY], Vc[R][NY];
-    double res = yv - md.c;
+    double res = hl ? yv - md.c[la] : 0.0;
+    {
+      double Hr[N];
+      gld_row<N>(md.H + la * N, Hr, md.vo);
 #pragma unroll
-    for (int q = 0; q < N; ++q) hrow[q] = 0.0;
-#pragma unroll
-    for (int s = 0; s < R; ++s)
-#pragma unroll
-      for (int q = 0; q < NY; ++q) Vc[s][q] = 0.0;
-#pragma unroll
-    for (int kk = 0; kk < N; ++kk) {
-      double t[N];
-      ld_row<N>(buf + CS::R0 + kk * RS, t);
-      const double h = md.H[kk];
-#pragma unroll
-      for (int q = 0; q < N; ++q) hrow[q] = fma(h, t[q], hrow[q]);
-      res = fma(-h, buf[CS::V0 + kk], res);
-#pragma unroll
-      for (int s = 0; s < R; ++s) {
-        const double fa = buf[CS::R1 + kk * RS + l + s * G];      // (F A)[kk][column l + s G]
-#pragma unroll
-        for (int q = 0; q < NY; ++q) Vc[s][q] = fma(buf[CS::HB + q * RS + kk], fa, Vc[s][q]);
+      for (int q = 0; q < N; ++q) {
+        Hr[q] = hl ? Hr[q] : 0.0;
+        hrow[q] = 0.0;
       }
-    }
 #pragma unroll
-    for (int q = 0; q < NY; ++q) hrow[N + q] = md.Rn[q];
+      for (int s = 0; s < R; ++s)
+#pragma unroll
+        for (int q = 0; q < NY; ++q) Vc[s][q] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < N; ++kk) {
+        double t[N];
+        ld_row<N>(buf + CS::R0 + kk * RS, t);
+        const double h = Hr[kk];
+#pragma unroll
+        for (int q = 0; q < N; ++q) hrow[q] = fma(h, t[q], hrow[q]);
+        res = fma(-h, buf[CS::V0 + kk], res);
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          const double fa = buf[CS::R1 + kk * RS + l + s * G];      // (F A)[kk][column l + s G]
+#pragma unroll
+          for (int q = 0; q < NY; ++q) Vc[s][q] = fma(md.H[q * N + kk], fa, Vc[s][q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NY; ++q) hrow[N + q] = hl ? md.R[la * NY + q] : 0.0;
+    }
 #pragma unroll
     for (int s = 0; s < R; ++s) {
 #pragma unroll

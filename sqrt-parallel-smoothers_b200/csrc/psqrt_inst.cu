@@ -238,8 +238,14 @@ struct NYImpl {
 #else
         auto kern = k_coop_filter_reduce<N, NY>;
 #endif
-        coop_smem(kern);
-        kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, CoopSweep<N>::smem_bytes(), st>>>(
+#if PSQ_COOP_ROWS2
+        constexpr size_t k1smem = coopr_k1_smem_bytes<N, NY>();   // + the model bank
+#else
+        constexpr size_t k1smem = CoopSweep<N>::smem_bytes();
+#endif
+        static_assert(k1smem <= 113 * 1024, "two CTAs of K1 per SM");
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1smem);
+        kern<<<coop_grid(Ppad, B), kCChunks * kCoopLanes, k1smem, st>>>(
             a, T, K, Ppad, chunk_own, chunk_pref, coop_vec(a, true, 0, 0, 0, 0));
       }
       unit_scan<CoopF2<N>, FElem<N>::NF, false>(chunk_pref, Ppad, B, warp_tot, counter, fuse_ctr, st);
